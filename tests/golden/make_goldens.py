@@ -1,0 +1,242 @@
+# -*- coding: utf-8 -*-
+''' Golden-vector generator: runs the UNMODIFIED reference (/root/reference, through
+    `_refshim`) and stores its outputs as small fixtures next to this script.
+
+    Build container only -- /root/reference does not exist on the GPU box.
+
+        python tests/golden/make_goldens.py points      # known-answer points, all neurons
+        python tests/golden/make_goldens.py rates       # rate functions on a Vm sweep
+        python tests/golden/make_goldens.py c1          # BASELINE config 1 (1000 points)
+        python tests/golden/make_goldens.py neurons     # small grids for the C3-C5 neurons
+        python tests/golden/make_goldens.py c2sub       # stratified subsample of RS-4D (C2)
+        python tests/golden/make_goldens.py all
+
+    Every record is produced by `NeuronalBilayerSonophore.computeEffVars`
+    (PySONIC/core/nbls.py:153-222); cycle counts are read off the solver by wrapping
+    `PeriodicSolver.integrateCycle` (solvers.py:332-334), RHS-call counts by wrapping
+    `BilayerSonophore.derivatives` (bls.py:681).
+'''
+
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _refshim import load_reference  # noqa: E402
+
+load_reference()
+import PySONIC.core.solvers as _solvers  # noqa: E402
+import PySONIC.core.bls as _bls  # noqa: E402
+from PySONIC.core import NeuronalBilayerSonophore, AcousticDrive  # noqa: E402
+from PySONIC.neurons import getPointNeuron  # noqa: E402
+
+_counters = {'ncycles': 0, 'nfe': 0}
+_orig_cycle = _solvers.PeriodicSolver.integrateCycle
+_orig_der = _bls.BilayerSonophore.derivatives
+
+
+def _cycle(self):
+    _counters['ncycles'] += 1
+    return _orig_cycle(self)
+
+
+def _der(self, *a, **k):
+    _counters['nfe'] += 1
+    return _orig_der(self, *a, **k)
+
+
+_solvers.PeriodicSolver.integrateCycle = _cycle
+_bls.BilayerSonophore.derivatives = _der
+
+_nbls_cache = {}
+
+
+def _nbls(name, a):
+    key = (name, a)
+    if key not in _nbls_cache:
+        _nbls_cache[key] = NeuronalBilayerSonophore(a, getPointNeuron(name))
+    return _nbls_cache[key]
+
+
+def run_point(args):
+    ''' :return: dict with effvars (one dict per fs), ncycles, nfe, tcomp '''
+    name, a, f, A, Q, fs = args
+    nbls = _nbls(name, a)
+    _counters['ncycles'] = 0
+    _counters['nfe'] = 0
+    t0 = time.perf_counter()
+    effvars, _ = nbls.computeEffVars(AcousticDrive(float(f), float(A)), np.asarray(fs, float),
+                                     float(Q))
+    tcomp = time.perf_counter() - t0
+    return {
+        'neuron': name, 'a': a, 'f': f, 'A': A, 'Q': Q, 'fs': list(map(float, fs)),
+        'ncycles': _counters['ncycles'], 'nfe': _counters['nfe'], 'tcomp': tcomp,
+        'effvars': [{k: float(v) for k, v in ev.items()} for ev in effvars],
+    }
+
+
+def pmap(jobs, nproc=None):
+    nproc = nproc or mp.cpu_count()
+    with mp.get_context('fork').Pool(nproc) as pool:
+        return pool.map(run_point, jobs, chunksize=1)
+
+
+def default_charges(name):
+    pn = getPointNeuron(name)
+    Qmin, Qmax = pn.Qbounds
+    return np.arange(Qmin, Qmax + 1e-5, 1e-5)   # run_lookups.py:196-199
+
+
+def c2_amps():
+    return np.insert(np.logspace(np.log10(0.1), np.log10(600), num=50), 0, 0.0) * 1e3
+
+
+# ---------------------------------------------------------------------------------------------
+
+def gen_points():
+    ''' Known-answer points: SURVEY Appendix A set + corners + fs vectors. '''
+    jobs = [
+        ('RS', 32e-9, 500e3, 100e3, -71.9e-5, [1.0]),
+        ('RS', 32e-9, 500e3, 600e3, 50e-5, [1.0]),
+        ('RS', 16e-9, 20e3, 50e3, -107e-5, [1.0]),
+        ('RS', 64e-9, 4e6, 300e3, 0.0, [1.0]),
+        ('RS', 32e-9, 500e3, 100e3, -71.9e-5, [0.5]),
+        ('RS', 32e-9, 500e3, 0.0, -71.9e-5, [1.0]),
+        ('RS', 32e-9, 500e3, 1e3, -50e-5, [1.0]),
+        ('RS', 32e-9, 1e6, 300e3, -30e-5, [1.0]),
+        ('RS', 16e-9, 4e6, 600e3, -107e-5, [1.0]),
+        ('RS', 64e-9, 20e3, 100e3, 50e-5, [1.0]),
+        ('RS', 64e-9, 4e6, 600e3, 50e-5, [1.0]),
+        ('RS', 32e-9, 100e3, 20e3, 10e-5, [1.0]),
+        ('RS', 32e-9, 2e6, 5e3, -71.9e-5, [1.0]),
+        ('RS', 32e-9, 3e6, 600e3, -107e-5, [1.0]),
+        ('STN', 32e-9, 500e3, 100e3, -58e-5, [0.75]),
+        ('STN', 32e-9, 500e3, 300e3, -93e-5, [0.01, 0.25, 0.5, 0.75, 1.0]),
+        ('STN', 32e-9, 500e3, 50e3, 20e-5, list(np.arange(1, 101) * 1e-2)),
+        ('FHnode', 32e-9, 500e3, 100e3, -140e-5, [1.0]),
+        ('FHnode', 32e-9, 4e6, 600e3, 100e-5, [1.0]),
+        ('SWnode', 32e-9, 500e3, 100e3, -200e-5, [1.0]),
+        ('SWnode', 32e-9, 100e3, 300e3, -287.5e-5, [1.0]),
+        ('MRGnode', 32e-9, 500e3, 100e3, -160e-5, [1.0]),
+        ('MRGnode', 32e-9, 2e6, 400e3, 100e-5, [1.0]),
+        ('SUseg', 32e-9, 500e3, 100e3, -60e-5, [1.0]),
+        ('SUseg', 32e-9, 1e6, 600e3, -95e-5, [1.0]),
+        ('RE', 32e-9, 500e3, 300e3, -89.5e-5, [1.0]),
+        ('RE', 32e-9, 4e6, 600e3, -124e-5, [1.0]),
+        ('RE', 32e-9, 20e3, 50e3, 50e-5, [1.0]),
+        ('TC', 32e-9, 500e3, 300e3, -61.93e-5, [1.0]),
+        ('TC', 32e-9, 500e3, 600e3, -97e-5, [1.0]),
+        ('TC', 32e-9, 4e6, 50e3, 50e-5, [1.0]),
+        ('FS', 32e-9, 500e3, 100e3, -71.4e-5, [1.0]),
+        ('LTS', 32e-9, 500e3, 100e3, -54e-5, [1.0]),
+        ('IB', 32e-9, 500e3, 100e3, -71.4e-5, [1.0]),
+    ]
+    recs = pmap(jobs)
+    # constants of the sonophore instances, for the host-side parameter tests
+    consts = {}
+    for name, a in sorted({(j[0], j[1]) for j in jobs}):
+        nb = _nbls(name, a)
+        consts[f'{name}@{a * 1e9:.0f}nm'] = {
+            'Delta': nb.Delta, 'ng0': nb.ng0, 'V0': nb.V0, 'Zmin': nb.Zmin, 'S0': nb.S0,
+            'Cm0': nb.Cm0, 'Qm0': nb.Qm0, 'LJ': nb.LJ_approx,
+            'Qbounds': list(map(float, nb.pneuron.Qbounds)), 'rates': list(nb.pneuron.rates)}
+    # a few initial deflections (bls.py:720-725)
+    z0 = []
+    for name, a, f, A, Q in [('RS', 32e-9, 500e3, 100e3, -71.9e-5), ('RS', 32e-9, 20e3, 100e3, -71.9e-5),
+                             ('RS', 16e-9, 500e3, 600e3, 50e-5), ('RS', 64e-9, 4e6, 0., 0.),
+                             ('SWnode', 32e-9, 500e3, 600e3, -287.5e-5)]:
+        nb = _nbls(name, a)
+        drive = AcousticDrive(f, A)
+        z0.append({'neuron': name, 'a': a, 'f': f, 'A': A, 'Q': Q,
+                   'Z0': float(nb.computeInitialDeflection(drive, Q, drive.dt))})
+    with open(os.path.join(HERE, 'points.json'), 'w') as fh:
+        json.dump({'points': recs, 'consts': consts, 'Z0': z0}, fh, indent=1)
+    print('points.json:', len(recs), 'points')
+
+
+def gen_rates():
+    ''' Every tabulated rate function of every supported neuron on a Vm sweep that includes
+        the singular / branch points (vtrap 0/0, tauu branch). '''
+    names = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg']
+    Vm = np.concatenate([np.linspace(-450., 350., 401),
+                         np.array([-43.2, -16.2, -41.2, -48.0, -57.0, -35.0, -61.0, -27.0,
+                                   -21.4, -25.7, -114.0, -80.0, -73.0, -87.0 + 7.0, -83.0,
+                                   -46.9, -18.9, -58.9, -10.9])])
+    out = {'Vm': Vm.tolist(), 'neurons': {}}
+    with np.errstate(all='ignore'):
+        for n in names:
+            pn = getPointNeuron(n)
+            tab = {}
+            for k, fn in pn.effRates().items():
+                tab[k] = [float(fn(np.float64(v))) for v in Vm]
+            out['neurons'][n] = {'rates': list(pn.rates), 'Cm0': pn.Cm0, 'Vm0': pn.Vm0, 'values': tab}
+    with open(os.path.join(HERE, 'rates_sweep.json'), 'w') as fh:
+        json.dump(out, fh)
+    print('rates_sweep.json:', len(names), 'neurons x', Vm.size, 'potentials')
+
+
+def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref):
+    jobs = [(name, a, f, A, Q, list(fsref)) for a in aref for f in fref for A in Aref for Q in Qref]
+    t0 = time.perf_counter()
+    recs = pmap(jobs)
+    wall = time.perf_counter() - t0
+    dims = (len(aref), len(fref), len(Aref), len(Qref), len(fsref))
+    keys = list(recs[0]['effvars'][0].keys())
+    tables = {k: np.array([ev[k] for r in recs for ev in r['effvars']]).reshape(dims) for k in keys}
+    np.savez_compressed(
+        os.path.join(HERE, fname), neuron=name, a=np.array(aref), f=np.array(fref),
+        A=np.array(Aref), Q=np.array(Qref), fs=np.array(fsref), keys=np.array(keys),
+        ncycles=np.array([r['ncycles'] for r in recs]).reshape(dims[:-1]),
+        nfe=np.array([r['nfe'] for r in recs]).reshape(dims[:-1]),
+        tcomp=np.array([r['tcomp'] for r in recs]).reshape(dims[:-1]),
+        wall_s=wall, nproc=mp.cpu_count(), **{f'tab_{k}': v for k, v in tables.items()})
+    print(f'{fname}: {len(jobs)} points in {wall:.1f} s on {mp.cpu_count()} processes')
+
+
+def gen_c1():
+    ''' BASELINE config 1 (SURVEY 8d "C1"). '''
+    A = np.insert(np.logspace(np.log10(0.1), np.log10(600), 19), 0, 0.) * 1e3
+    Q = np.linspace(-107e-5, 50e-5, 50)
+    _grid_to_npz('c1_RS_32nm_500kHz.npz', 'RS', [32e-9], [500e3], A, Q, [1.0])
+
+
+def gen_neurons():
+    ''' Small grids for the neurons of BASELINE configs 3-5. '''
+    Aall = c2_amps()
+    for name in ['FHnode', 'SWnode', 'MRGnode', 'SUseg']:
+        Q = default_charges(name)
+        _grid_to_npz(f'c4_{name}_sub.npz', name, [32e-9], [100e3, 500e3, 4e6],
+                     Aall[[0, 20, 36, 44, 50]], Q[::max(1, Q.size // 6)], [1.0])
+    for name in ['RE', 'TC']:
+        pn = getPointNeuron(name)
+        Qmin, Qmax = pn.Qbounds
+        Q = np.arange(Qmin, Qmax + 5e-6, 5e-6)
+        A = np.logspace(np.log10(50), np.log10(600), 26) * 1e3
+        _grid_to_npz(f'c5_{name}_sub.npz', name, [32e-9], [20e3, 500e3, 4e6],
+                     A[[0, 12, 25]], Q[::max(1, Q.size // 6)], [1.0])
+    Q = default_charges('STN')
+    _grid_to_npz('c3_STN_sub.npz', 'STN', [32e-9], [500e3], Aall[[0, 16, 30, 40, 50]],
+                 Q[::24], np.arange(1, 101)[::11] * 1e-2)
+
+
+def gen_c2sub():
+    ''' Stratified subsample of the RS 4-D default grid (SURVEY 8d "C2"). '''
+    A = c2_amps()[::7]            # 8 amplitudes incl. 0 and ~386 kPa
+    A = np.append(A, c2_amps()[-1])
+    Q = default_charges('RS')[::22]
+    _grid_to_npz('c2_RS_sub.npz', 'RS', [16e-9, 32e-9, 64e-9],
+                 [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0])
+
+
+if __name__ == '__main__':
+    what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
+            'c2sub': gen_c2sub}
+    for k, fn in todo.items():
+        if what in (k, 'all'):
+            fn()
