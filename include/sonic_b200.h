@@ -1,0 +1,145 @@
+/* sonic_b200.h -- C ABI of libsonic_b200.so, the B200-native SONIC lookup-table engine.
+ *
+ * Plain C, caller-owned buffers, no exceptions: every function returns 0 on success or a
+ * negative SONIC_E_* code, with a message retrievable through sonic_last_error().  There is
+ * no CPU fallback: without a CUDA device every compute entry point fails with
+ * SONIC_E_NODEVICE.
+ *
+ * The reference (tjjlemaire/PySONIC) is pure Python and has no FFI; these entry points are
+ * what a binding for its lookup-generation path replaces (citations relative to the
+ * reference tree):
+ *
+ *   sonic_lookup_run   <- scripts/run_lookups.py:98-172  (queue construction, one
+ *                         Batch(nbls.computeEffVars, queue) per radius, reshape to
+ *                         (na, nf, nA, nQ, nfs) tables) together with everything below it:
+ *                         PySONIC/core/batches.py:135-153 (Batch.run),
+ *                         PySONIC/core/nbls.py:153-222 (computeEffVars),
+ *                         PySONIC/core/bls.py:749-789 (simCycles), :681-718 (derivatives),
+ *                         :555-573 (balancedefQS), :334-349 (capacitance),
+ *                         PySONIC/core/solvers.py:336-365 (PeriodicSolver.solve),
+ *                         :317-330 (isPeriodicallyStable), :150-170 (odeint call),
+ *                         PySONIC/core/pneuron.py:268-271 (getEffRates).
+ *   sonic_points_run   <- the same for an explicit list of (radius, f, A, Q) points: one
+ *                         NeuronalBilayerSonophore.computeEffVars(drive, fs, Qm) call per
+ *                         point (nbls.py:153); used by multi-process sharding.
+ *   sonic_plan_*       <- split form of sonic_points_run (upload / launch / fetch) so that a
+ *                         caller can keep inputs resident on the device and time the kernels.
+ *   sonic_mean_rates   <- PointNeuron.getEffRates(Vm) (pneuron.py:268-271).
+ *   sonic_eval_rates   <- the neuron's alphax/betax/xinf/taux methods evaluated elementwise
+ *                         (PySONIC/neurons/*.py), for testing the generated device functions.
+ *   sonic_neuron_*     <- PySONIC/neurons/__init__.py:24-44 (getPointNeuron) and
+ *                         `pneuron.rates` (translators.py:411).
+ */
+#ifndef SONIC_B200_H
+#define SONIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONIC_ABI_VERSION 1
+
+#define SONIC_OK 0
+#define SONIC_E_NODEVICE (-1)   /* no CUDA device / bad device index */
+#define SONIC_E_CUDA (-2)       /* CUDA runtime error */
+#define SONIC_E_ARG (-3)        /* invalid argument */
+#define SONIC_E_NEURON (-4)     /* unknown neuron id */
+#define SONIC_E_ALLOC (-5)      /* allocation failure */
+
+/* Per-point status bits (out_status). */
+#define SONIC_STATUS_NOCONV 1u    /* periodic criterion not met at the 11-cycle cap */
+#define SONIC_STATUS_ZCLAMP 2u    /* deflection clamped at Zmin in the RHS */
+#define SONIC_STATUS_MXSTEP 4u    /* > 500 integrator steps within one output interval */
+#define SONIC_STATUS_STEPFAIL 8u  /* repeated error-test / corrector failures */
+#define SONIC_STATUS_Z0FAIL 16u   /* no quasi-static equilibrium deflection */
+#define SONIC_STATUS_TOLSF 32u    /* tolerance below machine precision */
+
+/* Constants of one bilayer sonophore (one per radius of the lookup).
+ * Reference: BilayerSonophore.__init__ / computePMparams, bls.py:115-137,457-470. */
+typedef struct {
+    double a;      /* in-plane radius (m) */
+    double Delta;  /* equilibrium inter-leaflet gap (m) */
+    double x0;     /* Lennard-Jones fit of the average intermolecular pressure ... */
+    double C;
+    double nrep;
+    double nattr;
+    double Cm0;    /* resting membrane capacitance (F/m2) */
+    double depth;  /* embedding tissue depth (m), 0 for a free sonophore */
+} SonicBlsParams;
+
+/* Aggregate statistics of one run (all devices summed unless noted). */
+typedef struct {
+    uint64_t n_points;      /* ODE points integrated */
+    uint64_t n_rhs;         /* right-hand-side evaluations (integrator ticks) */
+    uint64_t n_jac;         /* finite-difference Jacobian evaluations */
+    uint64_t n_steps;       /* accepted integrator steps */
+    uint64_t n_cycles;      /* acoustic cycles simulated */
+    uint64_t n_launches;    /* kernels launched */
+    double ms_z0;           /* kernel time: initial deflection (max over devices) */
+    double ms_integrate;    /* kernel time: batched integrator */
+    double ms_average;      /* kernel time: fused cycle averaging */
+    double ms_total;        /* upload + kernels + download (host wall clock) */
+} SonicStats;
+
+int sonic_version(void);
+int sonic_device_count(void);
+/* Copies the last error message of the calling thread into buf; returns its length. */
+int sonic_last_error(char* buf, int len);
+
+int sonic_neuron_count(void);
+int sonic_neuron_id(const char* name);                 /* -1 if unknown */
+int sonic_neuron_name(int id, char* buf, int len);
+int sonic_neuron_nrates(int id);
+int sonic_neuron_rate_name(int id, int i, char* buf, int len);
+
+/* out[r * n + k] = rate r of neuron `id` at potential Vm[k] (mV). */
+int sonic_eval_rates(int device, int id, const double* Vm, int64_t n, double* out);
+/* out[r] = mean over k of rate r at Vm[k]. */
+int sonic_mean_rates(int device, int id, const double* Vm, int64_t n, double* out);
+
+/* Effective variables for an explicit list of points.
+ *   ia[n], f[n], A[n], Q[n]  : radius index, frequency (Hz), amplitude (Pa), charge (C/m2)
+ *   fs[nfs]                  : coverage fractions
+ *   out_tables               : [1 + nrates][n][nfs]  ('V' first, then rates in neuron order)
+ *   out_ncycles[n], out_status[n], out_tpoint[n] (seconds of device time), out_nrhs[n]:
+ *                              any of these may be NULL
+ */
+int sonic_points_run(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                     const int32_t* ia, const double* f, const double* A, const double* Q,
+                     const double* fs, int nfs, double* out_tables, int32_t* out_ncycles,
+                     uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs,
+                     SonicStats* stats);
+
+/* Full grid, reference queue order a > f > A > Q (> fs): out_tables is
+ * [1 + nrates][na][nf][nA][nQ][nfs], the per-point outputs are [na][nf][nA][nQ].
+ * device_mask: bit d set = use device d (0 = device 0 only). */
+int sonic_lookup_run(const SonicBlsParams* radii, int na, const double* f, int nf,
+                     const double* A, int nA, const double* Q, int nQ, const double* fs, int nfs,
+                     int neuron_id, uint32_t device_mask, double* out_tables,
+                     int32_t* out_ncycles, uint32_t* out_status, double* out_tpoint,
+                     SonicStats* stats);
+
+/* Split form: inputs stay resident on the device between launches. */
+typedef struct SonicPlan SonicPlan;
+int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                      const int32_t* ia, const double* f, const double* A, const double* Q,
+                      const double* fs, int nfs, SonicPlan** plan);
+int sonic_plan_launch(SonicPlan* plan);   /* asynchronous on the plan's stream */
+int sonic_plan_sync(SonicPlan* plan);
+int sonic_plan_fetch(SonicPlan* plan, double* out_tables, int32_t* out_ncycles,
+                     uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs);
+/* Last-cycle deflection profiles Z[n][1000] (m) of the last launch (bls.py:806-813). */
+int sonic_plan_fetch_zprofiles(SonicPlan* plan, double* out_z);
+int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
+int sonic_plan_destroy(SonicPlan* plan);
+
+/* Sustained FP64 FMA throughput of the device (TFLOP/s), measured with a register-resident
+ * DFMA kernel: the roofline denominator for the integrator. */
+int sonic_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONIC_B200_H */

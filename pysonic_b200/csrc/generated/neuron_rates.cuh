@@ -1,0 +1,306 @@
+// GENERATED FILE -- do not edit.  Produced by pysonic_b200/codegen.py from pysonic_b200/neurons.py.
+// Voltage-dependent rate constants (s^-1) of every supported point neuron, as device functions.
+#pragma once
+
+#define SONIC_N_NEURONS 11
+#define SONIC_MAX_RATES 18
+
+// x / (exp(x / y) - 1): naive form of the reference (pneuron.py:351-354), 0/0 at x = 0 kept.
+static __device__ __forceinline__ double vtrap(double x, double y) { return x / (exp(x / y) - 1); }
+
+template <int ID> struct SonicRates;
+
+// ---- RS ----
+template <> struct SonicRates<0> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -56.2;
+        const double TauMax = 0.608;
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_p = 1.0 / (1 + exp(-(Vm + 35) / 10));
+        const double tau_p = TauMax / (3.3 * exp((Vm + 35) / 20) + exp(-(Vm + 35) / 20));
+        r[6] = inf_p / tau_p;
+        r[7] = (1 - inf_p) / tau_p;
+        (void)VT;
+        (void)TauMax;
+    }
+};
+
+// ---- FS ----
+template <> struct SonicRates<1> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -57.9;
+        const double TauMax = 0.502;
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_p = 1.0 / (1 + exp(-(Vm + 35) / 10));
+        const double tau_p = TauMax / (3.3 * exp((Vm + 35) / 20) + exp(-(Vm + 35) / 20));
+        r[6] = inf_p / tau_p;
+        r[7] = (1 - inf_p) / tau_p;
+        (void)VT;
+        (void)TauMax;
+    }
+};
+
+// ---- LTS ----
+template <> struct SonicRates<2> {
+    static constexpr int N = 12;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -50.0;
+        const double TauMax = 4.0;
+        const double Vx = -7.0;
+        const double xs = exp(-(Vm + Vx + 132.0) / 16.7) + exp((Vm + Vx + 16.8) / 18.2);
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_p = 1.0 / (1 + exp(-(Vm + 35) / 10));
+        const double tau_p = TauMax / (3.3 * exp((Vm + 35) / 20) + exp(-(Vm + 35) / 20));
+        r[6] = inf_p / tau_p;
+        r[7] = (1 - inf_p) / tau_p;
+        const double inf_s = 1.0 / (1.0 + exp(-(Vm + Vx + 57.0) / 6.2));
+        const double tau_s = 1.0 / 3.7 * (0.612 + 1.0 / xs) * 1e-3;
+        r[8] = inf_s / tau_s;
+        r[9] = (1 - inf_s) / tau_s;
+        const double inf_u = 1.0 / (1.0 + exp((Vm + Vx + 81.0) / 4.0));
+        const double tau_u = ((Vm + Vx < -80.0) ? 1.0 / 3.7 * exp((Vm + Vx + 467.0) / 66.6) * 1e-3 : 1.0 / 3.7 * (exp(-(Vm + Vx + 22) / 10.5) + 28.0) * 1e-3);
+        r[10] = inf_u / tau_u;
+        r[11] = (1 - inf_u) / tau_u;
+        (void)VT;
+        (void)TauMax;
+        (void)Vx;
+    }
+};
+
+// ---- IB ----
+template <> struct SonicRates<3> {
+    static constexpr int N = 12;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -56.2;
+        const double TauMax = 0.608;
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_p = 1.0 / (1 + exp(-(Vm + 35) / 10));
+        const double tau_p = TauMax / (3.3 * exp((Vm + 35) / 20) + exp(-(Vm + 35) / 20));
+        r[6] = inf_p / tau_p;
+        r[7] = (1 - inf_p) / tau_p;
+        r[8] = 0.055 * vtrap(-(Vm + 27), 3.8) * 1e3;
+        r[9] = 0.94 * exp(-(Vm + 75) / 17) * 1e3;
+        r[10] = 0.000457 * exp(-(Vm + 13) / 50) * 1e3;
+        r[11] = 0.0065 / (exp(-(Vm + 15) / 28) + 1) * 1e3;
+        (void)VT;
+        (void)TauMax;
+    }
+};
+
+// ---- RE ----
+template <> struct SonicRates<4> {
+    static constexpr int N = 10;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -67.0;
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_s = 1.0 / (1.0 + exp(-(Vm + 52.0) / 7.4));
+        const double tau_s = (1 + 0.33 / (exp((Vm + 27.0) / 10.0) + exp(-(Vm + 102.0) / 15.0))) * 1e-3;
+        r[6] = inf_s / tau_s;
+        r[7] = (1 - inf_s) / tau_s;
+        const double inf_u = 1.0 / (1.0 + exp((Vm + 80.0) / 5.0));
+        const double tau_u = (28.3 + 0.33 / (exp((Vm + 48.0) / 4.0) + exp(-(Vm + 407.0) / 50.0))) * 1e-3;
+        r[8] = inf_u / tau_u;
+        r[9] = (1 - inf_u) / tau_u;
+        (void)VT;
+    }
+};
+
+// ---- TC ----
+template <> struct SonicRates<5> {
+    static constexpr int N = 12;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -52.0;
+        const double Vx = 0.0;
+        const double xs = exp(-(Vm + Vx + 132.0) / 16.7) + exp((Vm + Vx + 16.8) / 18.2);
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        const double inf_s = 1.0 / (1.0 + exp(-(Vm + Vx + 57.0) / 6.2));
+        const double tau_s = 1.0 / 3.7 * (0.612 + 1.0 / xs) * 1e-3;
+        r[6] = inf_s / tau_s;
+        r[7] = (1 - inf_s) / tau_s;
+        const double inf_u = 1.0 / (1.0 + exp((Vm + Vx + 81.0) / 4.0));
+        const double tau_u = ((Vm + Vx < -80.0) ? 1.0 / 3.7 * exp((Vm + Vx + 467.0) / 66.6) * 1e-3 : 1.0 / 3.7 * (exp(-(Vm + Vx + 22) / 10.5) + 28.0) * 1e-3);
+        r[8] = inf_u / tau_u;
+        r[9] = (1 - inf_u) / tau_u;
+        const double inf_o = 1.0 / (1.0 + exp((Vm + 75.0) / 5.5));
+        const double tau_o = 1 / (exp(-14.59 - 0.086 * Vm) + exp(-1.87 + 0.0701 * Vm)) * 1e-3;
+        r[10] = inf_o / tau_o;
+        r[11] = (1 - inf_o) / tau_o;
+        (void)VT;
+        (void)Vx;
+    }
+};
+
+// ---- STN ----
+template <> struct SonicRates<6> {
+    static constexpr int N = 18;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double inf_a = 1 / (1 + exp((Vm - (-45)) / (-14.7)));
+        const double tau_a = 0.001 + 0.001 / (1 + exp(-(Vm - (-40)) / (-0.5)));
+        r[0] = inf_a / tau_a;
+        r[1] = (1 - inf_a) / tau_a;
+        const double inf_b = 1 / (1 + exp((Vm - (-90)) / (7.5)));
+        const double tau_b = 0.0 + 0.2 / (exp(-(Vm - (-60)) / (-30)) + exp(-(Vm - (-40)) / (10)));
+        r[2] = inf_b / tau_b;
+        r[3] = (1 - inf_b) / tau_b;
+        const double inf_c = 1 / (1 + exp((Vm - (-30.6)) / (-5)));
+        const double tau_c = 0.045 + 0.01 / (exp(-(Vm - (-27)) / (-20)) + exp(-(Vm - (-50)) / (15)));
+        r[4] = inf_c / tau_c;
+        r[5] = (1 - inf_c) / tau_c;
+        const double inf_d1 = 1 / (1 + exp((Vm - (-60)) / (7.5)));
+        const double tau_d1 = 0.4 + 0.5 / (exp(-(Vm - (-40)) / (-15)) + exp(-(Vm - (-20)) / (20)));
+        r[6] = inf_d1 / tau_d1;
+        r[7] = (1 - inf_d1) / tau_d1;
+        const double inf_m = 1 / (1 + exp((Vm - (-40)) / (-8)));
+        const double tau_m = 0.0002 + 0.003 / (1 + exp(-(Vm - (-53)) / (-0.7)));
+        r[8] = inf_m / tau_m;
+        r[9] = (1 - inf_m) / tau_m;
+        const double inf_h = 1 / (1 + exp((Vm - (-45.5)) / (6.4)));
+        const double tau_h = 0.0 + 0.0245 / (exp(-(Vm - (-50)) / (-15)) + exp(-(Vm - (-50)) / (16)));
+        r[10] = inf_h / tau_h;
+        r[11] = (1 - inf_h) / tau_h;
+        const double inf_n = 1 / (1 + exp((Vm - (-41)) / (-14)));
+        const double tau_n = 0.0 + 0.011 / (exp(-(Vm - (-40)) / (-40)) + exp(-(Vm - (-40)) / (50)));
+        r[12] = inf_n / tau_n;
+        r[13] = (1 - inf_n) / tau_n;
+        const double inf_p = 1 / (1 + exp((Vm - (-56)) / (-6.7)));
+        const double tau_p = 0.005 + 0.00033 / (exp(-(Vm - (-27)) / (-10)) + exp(-(Vm - (-102)) / (15)));
+        r[14] = inf_p / tau_p;
+        r[15] = (1 - inf_p) / tau_p;
+        const double inf_q = 1 / (1 + exp((Vm - (-85)) / (5.8)));
+        const double tau_q = 0.0 + 0.4 / (exp(-(Vm - (-50)) / (-15)) + exp(-(Vm - (-50)) / (16)));
+        r[16] = inf_q / tau_q;
+        r[17] = (1 - inf_q) / tau_q;
+    }
+};
+
+// ---- FHnode ----
+template <> struct SonicRates<7> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double q10 = 5.799546134795289;
+        const double V0 = -70.0;
+        r[0] = q10 * 0.36 * vtrap(22. - (Vm - V0), 3.) * 1e3;
+        r[1] = q10 * 0.4 * vtrap(Vm - V0 - 13., 20.) * 1e3;
+        r[2] = q10 * 0.1 * vtrap(Vm - V0 + 10.0, 6.) * 1e3;
+        r[3] = q10 * 4.5 / (exp((45. - (Vm - V0)) / 10.) + 1) * 1e3;
+        r[4] = q10 * 0.02 * vtrap(35. - (Vm - V0), 10.0) * 1e3;
+        r[5] = q10 * 0.05 * vtrap(Vm - V0 - 10., 10.) * 1e3;
+        r[6] = q10 * 0.006 * vtrap(40. - (Vm - V0), 10.0) * 1e3;
+        r[7] = q10 * 0.09 * vtrap(Vm - V0 + 25., 20.) * 1e3;
+        (void)q10;
+        (void)V0;
+    }
+};
+
+// ---- SWnode ----
+template <> struct SonicRates<8> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double am = (126 + 0.363 * Vm) / (1 + exp(-(Vm + 49) / 5.3)) * 1e3;
+        const double bh = 15.6 / (1 + exp(-(Vm + 56) / 10)) * 1e3;
+        r[0] = am;
+        r[1] = am / (exp((Vm + 56.2) / 4.17));
+        r[2] = bh / exp((Vm + 74.5) / 5);
+        r[3] = bh;
+    }
+};
+
+// ---- MRGnode ----
+template <> struct SonicRates<9> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double q10_mp = 3.530825783474764;
+        const double q10_h = 5.493344008948558;
+        const double q10_s = 1.0;
+        const double Vmh = Vm + 3.;
+        const double Vms = Vm - (-80.);
+        r[0] = q10_mp * 1.86 * vtrap(-(Vmh + 18.4), 10.3) * 1e3;
+        r[1] = q10_mp * 0.086 * vtrap(Vmh + 22.7, 9.16) * 1e3;
+        r[2] = q10_h * 0.062 * vtrap(Vmh + 111.0, 11.0) * 1e3;
+        r[3] = q10_h * 2.3 / (1 + exp(-(Vmh + 28.8) / 13.4)) * 1e3;
+        r[4] = q10_mp * 0.01 * vtrap(-(Vm + 27.), 10.2) * 1e3;
+        r[5] = q10_mp * 0.00025 * vtrap(Vm + 34., 10.) * 1e3;
+        r[6] = q10_s * 0.3 / (1 + exp(-(Vms - 27.) / 5.)) * 1e3;
+        r[7] = q10_s * 0.03 / (1 + exp(-(Vms + 10.) / 1.)) * 1e3;
+        (void)q10_mp;
+        (void)q10_h;
+        (void)q10_s;
+    }
+};
+
+// ---- SUseg ----
+template <> struct SonicRates<10> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double q10T = 1.9331820449317627;
+        const double q10BG = 1.9331820449317627;
+        const double FARADAY = 96485.3;
+        const double RgT = 2570.093793;
+        const double Vmm = (Vm - (-65.)) + (-6.0);
+        const double Vmhh = (Vm - (-65.)) + 6.0;
+        const double xn = (Vm - (-32.)) * FARADAY / RgT * 1e-3;
+        const double xl = (Vm - (-61.)) * FARADAY / RgT * 1e-3;
+        r[0] = q10T * 0.32 * vtrap((13.1 - Vmm), 4) * 1e3;
+        r[1] = q10T * 0.28 * vtrap((Vmm - 40.1), 5) * 1e3;
+        r[2] = q10T * 0.128 * exp((17.0 - Vmhh) / 18) * 1e3;
+        r[3] = q10T * 4 / (1 + exp((40.0 - Vmhh) / 5)) * 1e3;
+        r[4] = q10BG * (0.03 * exp(-(-5.) * 0.4 * xn)) * 1e3;
+        r[5] = q10BG * (0.03 * exp((-5.) * (1 - 0.4) * xn)) * 1e3;
+        r[6] = q10BG * (0.001 * exp(-(2.) * 1. * xl)) * 1e3;
+        r[7] = q10BG * (0.001 * exp((2.) * (1 - 1.) * xl)) * 1e3;
+        (void)q10T;
+        (void)q10BG;
+        (void)FARADAY;
+        (void)RgT;
+    }
+};
+
+static const char* const SONIC_NEURON_NAMES[SONIC_N_NEURONS] = {"RS", "FS", "LTS", "IB", "RE", "TC", "STN", "FHnode", "SWnode", "MRGnode", "SUseg"};
+static const int SONIC_NEURON_NRATES[SONIC_N_NEURONS] = {8, 8, 12, 12, 10, 12, 18, 8, 4, 8, 8};
+static const double SONIC_NEURON_CM0[SONIC_N_NEURONS] = {0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.02, 0.025, 0.02, 0.01};
+static const char* const SONIC_NEURON_RATE_NAMES[SONIC_N_NEURONS][SONIC_MAX_RATES] = {
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "alphas", "betas", "alphau", "betau", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "alphaq", "betaq", "alphar", "betar", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphas", "betas", "alphau", "betau", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphas", "betas", "alphau", "betau", "alphao", "betao", "", "", "", "", "", ""},
+    {"alphaa", "betaa", "alphab", "betab", "alphac", "betac", "alphad1", "betad1", "alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "alphaq", "betaq"},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "", "", "", "", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphap", "betap", "alphas", "betas", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphal", "betal", "", "", "", "", "", "", "", "", "", ""}
+};
+#define SONIC_DISPATCH_NEURON(id, CALL) switch (id) { case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; default: break; }

@@ -1,0 +1,794 @@
+// sonic_b200.cu -- CUDA kernels (sm_100a) and C ABI of the SONIC lookup-table engine.
+//
+// Kernels
+//   sonic_z0_kernel         initial quasi-static deflection of every point (one thread/point)
+//   sonic_integrate_kernel  persistent batched integrator: one lane per grid point, lanes
+//                           refill themselves from a cost-sorted work queue; every tick = one
+//                           warp-convergent RHS evaluation + per-lane controller bookkeeping;
+//                           periodic-convergence test on the fly against the previous cycle
+//   sonic_average_kernel    fused cycle averaging: Z(t) -> Cm -> per coverage fraction V(t)
+//                           -> generated neuron rate functions -> warp-shuffle means
+//   sonic_rates_kernel      elementwise / mean evaluation of the generated rate functions
+//   sonic_dfma_kernel       FP64 FMA throughput microbenchmark (roofline denominator)
+//
+// Host side: plan objects (device buffers + stream + events), cost model for the work queue
+// order, multi-device fan-out for sonic_lookup_run.  See include/sonic_b200.h for the ABI.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/sonic_b200.h"
+#include "generated/neuron_rates.cuh"
+#include "sonic_core.h"
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int set_err(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return set_err(SONIC_E_CUDA, "%s failed: %s (%s:%d)", #expr,                     \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device code
+// ---------------------------------------------------------------------------------------
+#define SONIC_BLOCK 128
+#define SONIC_AVG_WARPS 4
+
+struct SonicJob {
+    const SonicBls* radii;
+    const int* order;          // work-queue order (cost-sorted point indices)
+    const int* ia;
+    const double* f;
+    const double* A;
+    const double* Q;
+    double* z0;
+    double* zbuf;              // [n][1000]
+    double* ngbuf;             // [slots][1000]
+    int* ncycles;
+    unsigned* status;
+    unsigned* nfe;
+    unsigned* nje;
+    unsigned* nsteps;
+    double* tpoint;
+    unsigned long long* counter;
+    long long n;
+    int lanes_per_warp;
+};
+
+__constant__ SonicTables c_tables;
+
+static __device__ __forceinline__ unsigned long long sonic_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(128) sonic_z0_kernel(SonicJob job) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= job.n) return;
+    SonicPoint p;
+    const double f = job.f[i];
+    sonic_point_init(p, job.radii[job.ia[i]], f, job.A[i], job.Q[i]);
+    double z0;
+    const bool ok = sonic_z0(p, f, &z0);
+    job.z0[i] = ok ? z0 : nan("");
+}
+
+__global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob job) {
+    __shared__ SonicTables tab;
+    {
+        const double* src = reinterpret_cast<const double*>(&c_tables);
+        double* dst = reinterpret_cast<double*>(&tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(SonicTables) / sizeof(double)); i += blockDim.x)
+            dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    SonicSink sink;
+    sink.ngbuf = job.ngbuf + slot * SONIC_NPC;
+    sink.zbuf = nullptr;
+    sink.stride = 1;
+
+    SonicLane s;
+    SonicPoint p;
+    long long pt = -1;
+    double period = 0.0;
+    unsigned long long t_start = 0;
+    bool can_work = lane < job.lanes_per_warp;
+
+    while (true) {
+        if (pt < 0 && can_work) {
+            // refill this lane from the work queue
+            const unsigned long long q = atomicAdd(job.counter, 1ULL);
+            if (q < (unsigned long long)job.n) {
+                pt = job.order[q];
+                const double f = job.f[pt];
+                sonic_point_init(p, job.radii[job.ia[pt]], f, job.A[pt], job.Q[pt]);
+                period = 1.0 / f;
+                sink.zbuf = job.zbuf + pt * SONIC_NPC;
+                const double z0 = job.z0[pt];
+                t_start = sonic_globaltimer();
+                if (z0 != z0) {
+                    // no quasi-static equilibrium: report and move on
+                    job.ncycles[pt] = 0;
+                    job.status[pt] = SONIC_ST_Z0FAIL;
+                    job.nfe[pt] = 0; job.nje[pt] = 0; job.nsteps[pt] = 0;
+                    job.tpoint[pt] = 0.0;
+                    pt = -1;
+                } else {
+                    sonic_lane_start(s, p, f, z0, sink);
+                }
+            } else {
+                can_work = false;
+            }
+        }
+        const bool active = pt >= 0;
+        if (!__any_sync(0xffffffffu, active || can_work)) break;
+        if (active) {
+            double fv[3];
+            if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
+            sonic_tick(s, &tab, sink, period, fv);
+            if (s.phase == PH_DONE) {
+                job.ncycles[pt] = s.cyc;
+                job.status[pt] = s.status;
+                job.nfe[pt] = s.nfe;
+                job.nje[pt] = s.nje;
+                job.nsteps[pt] = s.nsteps;
+                job.tpoint[pt] = (double)(sonic_globaltimer() - t_start) * 1e-9;
+                pt = -1;
+            }
+        }
+    }
+}
+
+// Fused cycle averaging.  One warp per ODE point; the point's capacitance profile is staged in
+// shared memory and reused for every coverage fraction.
+template <int NID>
+__global__ void __launch_bounds__(32 * SONIC_AVG_WARPS)
+sonic_average_kernel(const double* __restrict__ zbuf, const int* __restrict__ ia,
+                     const double* __restrict__ Q, const SonicBls* __restrict__ radii,
+                     const unsigned* __restrict__ status, long long n,
+                     const double* __restrict__ fs, int nfs, double* __restrict__ out) {
+    constexpr int NR = SonicRates<NID>::N;
+    __shared__ double cm_s[SONIC_AVG_WARPS][SONIC_NPC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * SONIC_AVG_WARPS;
+    for (long long pt = (long long)blockIdx.x * SONIC_AVG_WARPS + warp; pt < n; pt += nwarps) {
+        const SonicBls b = radii[ia[pt]];
+        const double a2 = b.a * b.a;
+        const double q = Q[pt];
+        const bool bad = (status[pt] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
+                                        SONIC_ST_TOLSF)) != 0;
+        const double* z = zbuf + pt * SONIC_NPC;
+        double* cm = cm_s[warp];
+        for (int k = lane; k < SONIC_NPC; k += 32) cm[k] = sonic_capacitance(a2, b.Delta, b.Cm0, z[k]);
+        __syncwarp();
+        for (int j = 0; j < nfs; j++) {
+            const double x = fs[j];
+            double acc[1 + NR];
+#pragma unroll
+            for (int v = 0; v <= NR; v++) acc[v] = 0.0;
+            for (int k = lane; k < SONIC_NPC; k += 32) {
+                // spatial average of the capacitance, then membrane potential in mV
+                const double vm = q / (x * cm[k] + (1 - x) * b.Cm0) * 1e3;   // nbls.py:148-151,188
+                double r[NR];
+                SonicRates<NID>::eval(vm, r);
+                acc[0] += vm;
+#pragma unroll
+                for (int v = 0; v < NR; v++) acc[1 + v] += r[v];
+            }
+#pragma unroll
+            for (int v = 0; v <= NR; v++) {
+                double t = acc[v];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                acc[v] = t;
+            }
+            // lane v stores table v (mean over the 1000 samples of the cycle)
+            double mine = 0.0;
+#pragma unroll
+            for (int v = 0; v <= NR; v++)
+                if (lane == v) mine = acc[v];
+            if (lane <= NR)
+                out[((long long)lane * n + pt) * nfs + j] = bad ? nan("") : mine / (double)SONIC_NPC;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NID>
+__global__ void sonic_rates_kernel(const double* __restrict__ vm, long long n, double* __restrict__ out) {
+    constexpr int NR = SonicRates<NID>::N;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (long long)gridDim.x * blockDim.x) {
+        double r[NR];
+        SonicRates<NID>::eval(vm[k], r);
+#pragma unroll
+        for (int v = 0; v < NR; v++) out[(long long)v * n + k] = r[v];
+    }
+}
+
+// mean of each rate over a potential vector: single block, deterministic tree reduction
+template <int NID>
+__global__ void __launch_bounds__(256) sonic_mean_rates_kernel(const double* __restrict__ vm, long long n,
+                                                              double* __restrict__ out) {
+    constexpr int NR = SonicRates<NID>::N;
+    __shared__ double part[8][NR];
+    double acc[NR];
+#pragma unroll
+    for (int v = 0; v < NR; v++) acc[v] = 0.0;
+    for (long long k = threadIdx.x; k < n; k += blockDim.x) {
+        double r[NR];
+        SonicRates<NID>::eval(vm[k], r);
+#pragma unroll
+        for (int v = 0; v < NR; v++) acc[v] += r[v];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < NR; v++) {
+        double t = acc[v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) part[warp][v] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += part[w][threadIdx.x];
+        out[threadIdx.x] = t / (double)n;
+    }
+}
+
+// FP64 FMA peak: 8 independent register chains per thread.
+__global__ void __launch_bounds__(256) sonic_dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static SonicTables g_host_tables;
+static bool g_tables_ready = false;
+
+static int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(SONIC_E_NODEVICE, "no CUDA device available (%s): libsonic_b200 has no CPU path",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return set_err(SONIC_E_NODEVICE, "device %d out of range (0..%d)", device, count - 1);
+    return SONIC_OK;
+}
+
+// Predicted relative cost (log of RHS evaluations) of a point, used only to order the work
+// queue (longest first).  Least-squares fit on a stratified sample of the RS 4-D grid.
+static double predict_log_cost(double a, double f, double A) {
+    const double lf = log(f / 500e3), lA = log1p(A / 20e3), la = log(a / 32e-9);
+    const double noise = (A > 0. && A < 8e3) ? 1. : 0., zero = (A == 0.) ? 1. : 0.;
+    return 8.142 - 0.3655 * lf + 0.9828 * lA - 0.3437 * la + 0.2427 * noise - 0.534 * zero -
+           0.0237 * lf * lA - 0.1937 * noise * lf;
+}
+
+struct SonicPlan {
+    int device = 0;
+    int neuron_id = 0;
+    int nrates = 0;
+    int na = 0, nfs = 0;
+    long long n = 0;
+    long long slots = 0;
+    int grid = 0, lanes_per_warp = 32;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device buffers
+    SonicBls* d_radii = nullptr;
+    int *d_order = nullptr, *d_ia = nullptr, *d_ncycles = nullptr;
+    double *d_f = nullptr, *d_A = nullptr, *d_Q = nullptr, *d_fs = nullptr, *d_z0 = nullptr;
+    double *d_zbuf = nullptr, *d_ngbuf = nullptr, *d_tpoint = nullptr, *d_out = nullptr;
+    unsigned *d_status = nullptr, *d_nfe = nullptr, *d_nje = nullptr, *d_nsteps = nullptr;
+    unsigned long long* d_counter = nullptr;
+    uint64_t launches = 0;
+    double ms_upload = 0.0;
+    bool launched = false;
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+static int plan_free(SonicPlan* p) {
+    if (!p) return SONIC_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_radii); cudaFree(p->d_order); cudaFree(p->d_ia); cudaFree(p->d_ncycles);
+    cudaFree(p->d_f); cudaFree(p->d_A); cudaFree(p->d_Q); cudaFree(p->d_fs); cudaFree(p->d_z0);
+    cudaFree(p->d_zbuf); cudaFree(p->d_ngbuf); cudaFree(p->d_tpoint); cudaFree(p->d_out);
+    cudaFree(p->d_status); cudaFree(p->d_nfe); cudaFree(p->d_nje); cudaFree(p->d_nsteps);
+    cudaFree(p->d_counter);
+    for (auto& e : p->ev)
+        if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return SONIC_OK;
+}
+
+template <int NID>
+static void launch_average(SonicPlan* p, int blocks) {
+    sonic_average_kernel<NID><<<blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(
+        p->d_zbuf, p->d_ia, p->d_Q, p->d_radii, p->d_status, p->n, p->d_fs, p->nfs, p->d_out);
+}
+
+template <int NID>
+static void launch_rates(const double* vm, long long n, double* out, bool mean) {
+    if (mean)
+        sonic_mean_rates_kernel<NID><<<1, 256>>>(vm, n, out);
+    else
+        sonic_rates_kernel<NID><<<(int)std::min<long long>((n + 255) / 256, 4096), 256>>>(vm, n, out);
+}
+
+extern "C" {
+
+int sonic_version(void) { return SONIC_ABI_VERSION; }
+
+int sonic_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+int sonic_last_error(char* buf, int len) {
+    if (buf && len > 0) {
+        strncpy(buf, g_err.c_str(), len - 1);
+        buf[len - 1] = 0;
+    }
+    return (int)g_err.size();
+}
+
+int sonic_neuron_count(void) { return SONIC_N_NEURONS; }
+
+int sonic_neuron_id(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < SONIC_N_NEURONS; i++)
+        if (strcmp(name, SONIC_NEURON_NAMES[i]) == 0) return i;
+    return -1;
+}
+
+int sonic_neuron_name(int id, char* buf, int len) {
+    if (id < 0 || id >= SONIC_N_NEURONS) return set_err(SONIC_E_NEURON, "unknown neuron id %d", id);
+    if (buf && len > 0) {
+        strncpy(buf, SONIC_NEURON_NAMES[id], len - 1);
+        buf[len - 1] = 0;
+    }
+    return SONIC_OK;
+}
+
+int sonic_neuron_nrates(int id) {
+    if (id < 0 || id >= SONIC_N_NEURONS) return set_err(SONIC_E_NEURON, "unknown neuron id %d", id);
+    return SONIC_NEURON_NRATES[id];
+}
+
+int sonic_neuron_rate_name(int id, int i, char* buf, int len) {
+    if (id < 0 || id >= SONIC_N_NEURONS) return set_err(SONIC_E_NEURON, "unknown neuron id %d", id);
+    if (i < 0 || i >= SONIC_NEURON_NRATES[id]) return set_err(SONIC_E_ARG, "rate index %d out of range", i);
+    if (buf && len > 0) {
+        strncpy(buf, SONIC_NEURON_RATE_NAMES[id][i], len - 1);
+        buf[len - 1] = 0;
+    }
+    return SONIC_OK;
+}
+
+static int rates_common(int device, int id, const double* Vm, int64_t n, double* out, bool mean) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (id < 0 || id >= SONIC_N_NEURONS) return set_err(SONIC_E_NEURON, "unknown neuron id %d", id);
+    if (!Vm || !out || n <= 0) return set_err(SONIC_E_ARG, "invalid Vm/out/n");
+    CUDA_TRY(cudaSetDevice(device));
+    const int nr = SONIC_NEURON_NRATES[id];
+    double *d_vm = nullptr, *d_out = nullptr;
+    const size_t nout = mean ? (size_t)nr : (size_t)nr * n;
+    CUDA_TRY(dalloc(&d_vm, n));
+    CUDA_TRY(dalloc(&d_out, nout));
+    CUDA_TRY(cudaMemcpy(d_vm, Vm, n * sizeof(double), cudaMemcpyHostToDevice));
+#define CALL(ID) launch_rates<ID>(d_vm, n, d_out, mean)
+    SONIC_DISPATCH_NEURON(id, CALL)
+#undef CALL
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d_vm);
+    cudaFree(d_out);
+    return SONIC_OK;
+}
+
+int sonic_eval_rates(int device, int id, const double* Vm, int64_t n, double* out) {
+    return rates_common(device, id, Vm, n, out, false);
+}
+
+int sonic_mean_rates(int device, int id, const double* Vm, int64_t n, double* out) {
+    return rates_common(device, id, Vm, n, out, true);
+}
+
+int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                      const int32_t* ia, const double* f, const double* A, const double* Q,
+                      const double* fs, int nfs, SonicPlan** out_plan) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (neuron_id < 0 || neuron_id >= SONIC_N_NEURONS)
+        return set_err(SONIC_E_NEURON, "unknown neuron id %d", neuron_id);
+    if (!radii || na <= 0 || n <= 0 || !ia || !f || !A || !Q || !fs || nfs <= 0 || !out_plan)
+        return set_err(SONIC_E_ARG, "invalid argument (null pointer or empty dimension)");
+    if (n > 0x7fffffffLL) return set_err(SONIC_E_ARG, "too many points for one plan (%lld)", (long long)n);
+    for (int64_t i = 0; i < n; i++) {
+        if (ia[i] < 0 || ia[i] >= na) return set_err(SONIC_E_ARG, "radius index out of range at point %lld", (long long)i);
+        if (!(f[i] > 0.)) return set_err(SONIC_E_ARG, "frequency must be strictly positive (point %lld)", (long long)i);
+        if (!(A[i] >= 0.)) return set_err(SONIC_E_ARG, "amplitude must be positive or null (point %lld)", (long long)i);
+    }
+    for (int i = 0; i < na; i++)
+        if (!(radii[i].a > 0.) || !(radii[i].Delta > 0.) || !(radii[i].Cm0 > 0.))
+            return set_err(SONIC_E_ARG, "invalid sonophore constants for radius %d", i);
+    CUDA_TRY(cudaSetDevice(device));
+    if (!g_tables_ready) {
+        sonic_fill_tables(&g_host_tables);
+        g_tables_ready = true;
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_tables, &g_host_tables, sizeof(SonicTables)));
+
+    const auto t0 = std::chrono::steady_clock::now();
+    SonicPlan* p = new SonicPlan();
+    p->device = device;
+    p->neuron_id = neuron_id;
+    p->nrates = SONIC_NEURON_NRATES[neuron_id];
+    p->na = na;
+    p->nfs = nfs;
+    p->n = n;
+
+    // launch geometry of the persistent integrator
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    int blocks_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sonic_integrate_kernel,
+                                                           SONIC_BLOCK, 0));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const long long max_blocks = (long long)prop.multiProcessorCount * blocks_per_sm;
+    const long long warps_total = max_blocks * (SONIC_BLOCK / 32);
+    // few points: spread them over as many warps as possible (the chain of one point is
+    // serial, so idle lanes cost nothing while extra warps shorten the critical path)
+    long long lpw = (n + warps_total - 1) / warps_total;
+    if (lpw > 32) lpw = 32;
+    if (lpw < 1) lpw = 1;
+    p->lanes_per_warp = (int)lpw;
+    long long need_warps = (n + lpw - 1) / lpw;
+    long long blocks = (need_warps + (SONIC_BLOCK / 32) - 1) / (SONIC_BLOCK / 32);
+    if (blocks > max_blocks) blocks = max_blocks;
+    p->grid = (int)blocks;
+    p->slots = blocks * SONIC_BLOCK;
+
+    // work-queue order: predicted cost, longest first
+    std::vector<int> order(n);
+    std::vector<double> cost(n);
+    for (int64_t i = 0; i < n; i++) {
+        order[i] = (int)i;
+        cost[i] = predict_log_cost(radii[ia[i]].a, f[i], A[i]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+
+    std::vector<SonicBls> hb(na);
+    for (int i = 0; i < na; i++) {
+        hb[i].a = radii[i].a; hb[i].Delta = radii[i].Delta; hb[i].x0 = radii[i].x0; hb[i].C = radii[i].C;
+        hb[i].nrep = radii[i].nrep; hb[i].nattr = radii[i].nattr; hb[i].Cm0 = radii[i].Cm0;
+        hb[i].depth = radii[i].depth;
+    }
+    cudaError_t e = cudaSuccess;
+#define TRYA(x) if (e == cudaSuccess) e = (x)
+    TRYA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto& ev : p->ev) TRYA(cudaEventCreate(&ev));
+    TRYA(dalloc(&p->d_radii, na));
+    TRYA(dalloc(&p->d_order, n)); TRYA(dalloc(&p->d_ia, n)); TRYA(dalloc(&p->d_ncycles, n));
+    TRYA(dalloc(&p->d_f, n)); TRYA(dalloc(&p->d_A, n)); TRYA(dalloc(&p->d_Q, n));
+    TRYA(dalloc(&p->d_fs, nfs)); TRYA(dalloc(&p->d_z0, n));
+    TRYA(dalloc(&p->d_zbuf, (size_t)n * SONIC_NPC));
+    TRYA(dalloc(&p->d_ngbuf, (size_t)p->slots * SONIC_NPC));
+    TRYA(dalloc(&p->d_tpoint, n));
+    TRYA(dalloc(&p->d_out, (size_t)(1 + p->nrates) * n * nfs));
+    TRYA(dalloc(&p->d_status, n)); TRYA(dalloc(&p->d_nfe, n)); TRYA(dalloc(&p->d_nje, n));
+    TRYA(dalloc(&p->d_nsteps, n)); TRYA(dalloc(&p->d_counter, 1));
+    TRYA(cudaMemcpyAsync(p->d_radii, hb.data(), na * sizeof(SonicBls), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_ia, ia, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_f, f, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_A, A, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_Q, Q, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_fs, fs, nfs * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaStreamSynchronize(p->stream));
+#undef TRYA
+    if (e != cudaSuccess) {
+        plan_free(p);
+        return set_err(e == cudaErrorMemoryAllocation ? SONIC_E_ALLOC : SONIC_E_CUDA,
+                       "plan creation failed: %s", cudaGetErrorString(e));
+    }
+    p->ms_upload = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out_plan = p;
+    return SONIC_OK;
+}
+
+int sonic_plan_launch(SonicPlan* p) {
+    if (!p) return set_err(SONIC_E_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    SonicJob job;
+    job.radii = p->d_radii; job.order = p->d_order; job.ia = p->d_ia; job.f = p->d_f; job.A = p->d_A;
+    job.Q = p->d_Q; job.z0 = p->d_z0; job.zbuf = p->d_zbuf; job.ngbuf = p->d_ngbuf;
+    job.ncycles = p->d_ncycles; job.status = p->d_status; job.nfe = p->d_nfe; job.nje = p->d_nje;
+    job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
+    job.lanes_per_warp = p->lanes_per_warp;
+    CUDA_TRY(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), p->stream));
+    CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
+    sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);
+    CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
+    sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, 0, p->stream>>>(job);
+    CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
+    {
+        long long blocks = (p->n + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
+        if (blocks > 148LL * 64) blocks = 148LL * 64;
+#define CALL(ID) launch_average<ID>(p, (int)blocks)
+        SONIC_DISPATCH_NEURON(p->neuron_id, CALL)
+#undef CALL
+    }
+    CUDA_TRY(cudaEventRecord(p->ev[3], p->stream));
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 3;
+    p->launched = true;
+    return SONIC_OK;
+}
+
+int sonic_plan_sync(SonicPlan* p) {
+    if (!p) return set_err(SONIC_E_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SONIC_OK;
+}
+
+int sonic_plan_fetch(SonicPlan* p, double* out_tables, int32_t* out_ncycles, uint32_t* out_status,
+                     double* out_tpoint, uint32_t* out_nrhs) {
+    if (!p || !p->launched) return set_err(SONIC_E_ARG, "plan not launched");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t n = p->n;
+    if (out_tables)
+        CUDA_TRY(cudaMemcpyAsync(out_tables, p->d_out, (size_t)(1 + p->nrates) * n * p->nfs * sizeof(double),
+                                 cudaMemcpyDeviceToHost, p->stream));
+    if (out_ncycles)
+        CUDA_TRY(cudaMemcpyAsync(out_ncycles, p->d_ncycles, n * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    if (out_status)
+        CUDA_TRY(cudaMemcpyAsync(out_status, p->d_status, n * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
+    if (out_tpoint)
+        CUDA_TRY(cudaMemcpyAsync(out_tpoint, p->d_tpoint, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (out_nrhs)
+        CUDA_TRY(cudaMemcpyAsync(out_nrhs, p->d_nfe, n * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SONIC_OK;
+}
+
+int sonic_plan_fetch_zprofiles(SonicPlan* p, double* out_z) {
+    if (!p || !p->launched || !out_z) return set_err(SONIC_E_ARG, "plan not launched or null buffer");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaMemcpyAsync(out_z, p->d_zbuf, (size_t)p->n * SONIC_NPC * sizeof(double),
+                             cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SONIC_OK;
+}
+
+int sonic_plan_stats(SonicPlan* p, SonicStats* st) {
+    if (!p || !p->launched || !st) return set_err(SONIC_E_ARG, "plan not launched or null stats");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    memset(st, 0, sizeof(*st));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1])); st->ms_z0 = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[1], p->ev[2])); st->ms_integrate = ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p->ev[2], p->ev[3])); st->ms_average = ms;
+    const size_t n = p->n;
+    std::vector<unsigned> nfe(n), nje(n), nst(n);
+    std::vector<int> ncyc(n);
+    CUDA_TRY(cudaMemcpy(nfe.data(), p->d_nfe, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(nje.data(), p->d_nje, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(nst.data(), p->d_nsteps, n * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ncyc.data(), p->d_ncycles, n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+        st->n_rhs += nfe[i]; st->n_jac += nje[i]; st->n_steps += nst[i]; st->n_cycles += ncyc[i];
+    }
+    st->n_points = n;
+    st->n_launches = p->launches;
+    st->ms_total = p->ms_upload;
+    return SONIC_OK;
+}
+
+int sonic_plan_destroy(SonicPlan* p) { return plan_free(p); }
+
+int sonic_points_run(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                     const int32_t* ia, const double* f, const double* A, const double* Q,
+                     const double* fs, int nfs, double* out_tables, int32_t* out_ncycles,
+                     uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    SonicPlan* p = nullptr;
+    int rc = sonic_plan_create(device, radii, na, neuron_id, n, ia, f, A, Q, fs, nfs, &p);
+    if (rc) return rc;
+    rc = sonic_plan_launch(p);
+    if (!rc) rc = sonic_plan_fetch(p, out_tables, out_ncycles, out_status, out_tpoint, out_nrhs);
+    if (!rc && stats) {
+        rc = sonic_plan_stats(p, stats);
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    plan_free(p);
+    return rc;
+}
+
+int sonic_lookup_run(const SonicBlsParams* radii, int na, const double* f, int nf, const double* A,
+                     int nA, const double* Q, int nQ, const double* fs, int nfs, int neuron_id,
+                     uint32_t device_mask, double* out_tables, int32_t* out_ncycles,
+                     uint32_t* out_status, double* out_tpoint, SonicStats* stats) {
+    if (!radii || !f || !A || !Q || !fs || na <= 0 || nf <= 0 || nA <= 0 || nQ <= 0 || nfs <= 0 || !out_tables)
+        return set_err(SONIC_E_ARG, "invalid argument (null pointer or empty dimension)");
+    if (neuron_id < 0 || neuron_id >= SONIC_N_NEURONS)
+        return set_err(SONIC_E_NEURON, "unknown neuron id %d", neuron_id);
+    const int ndev_avail = sonic_device_count();
+    if (ndev_avail == 0) return check_device(0);
+    std::vector<int> devs;
+    if (device_mask == 0) device_mask = 1;
+    for (int d = 0; d < 32; d++)
+        if (device_mask & (1u << d)) {
+            if (d >= ndev_avail) return set_err(SONIC_E_NODEVICE, "device %d in mask but only %d present", d, ndev_avail);
+            devs.push_back(d);
+        }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int64_t n = (int64_t)na * nf * nA * nQ;
+    const int nvar = 1 + SONIC_NEURON_NRATES[neuron_id];
+    // flatten the grid in the reference's queue order: a > f > A > Q
+    std::vector<int32_t> pia(n);
+    std::vector<double> pf(n), pA(n), pQ(n);
+    int64_t i = 0;
+    for (int x = 0; x < na; x++)
+        for (int y = 0; y < nf; y++)
+            for (int z = 0; z < nA; z++)
+                for (int w = 0; w < nQ; w++, i++) {
+                    pia[i] = x; pf[i] = f[y]; pA[i] = A[z]; pQ[i] = Q[w];
+                }
+    const int nd = (int)devs.size();
+    if (nd == 1) {
+        int rc = sonic_points_run(devs[0], radii, na, neuron_id, n, pia.data(), pf.data(), pA.data(), pQ.data(),
+                                  fs, nfs, out_tables, out_ncycles, out_status, out_tpoint, nullptr, stats);
+        if (!rc && stats)
+            stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
+    // several devices: deal the cost-sorted points round-robin so every device gets the same
+    // cost profile, one host thread per device, host-side scatter of the results
+    std::vector<int> order(n);
+    std::vector<double> cost(n);
+    for (int64_t k = 0; k < n; k++) {
+        order[k] = (int)k;
+        cost[k] = predict_log_cost(radii[pia[k]].a, pf[k], pA[k]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    struct Shard {
+        std::vector<int> idx;
+        std::vector<int32_t> ia, ncyc;
+        std::vector<double> f, A, Q, out, tp;
+        std::vector<uint32_t> st;
+        SonicStats stats;
+        int rc = 0;
+        std::string err;
+    };
+    std::vector<Shard> sh(nd);
+    for (int64_t k = 0; k < n; k++) sh[k % nd].idx.push_back(order[k]);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++) {
+        Shard& s = sh[d];
+        const size_t m = s.idx.size();
+        s.ia.resize(m); s.f.resize(m); s.A.resize(m); s.Q.resize(m);
+        s.out.resize((size_t)nvar * m * nfs); s.ncyc.resize(m); s.st.resize(m); s.tp.resize(m);
+        for (size_t k = 0; k < m; k++) {
+            const int g = s.idx[k];
+            s.ia[k] = pia[g]; s.f[k] = pf[g]; s.A[k] = pA[g]; s.Q[k] = pQ[g];
+        }
+        th.emplace_back([&, d]() {
+            Shard& s2 = sh[d];
+            if (s2.idx.empty()) return;
+            s2.rc = sonic_points_run(devs[d], radii, na, neuron_id, (int64_t)s2.idx.size(), s2.ia.data(),
+                                     s2.f.data(), s2.A.data(), s2.Q.data(), fs, nfs, s2.out.data(),
+                                     s2.ncyc.data(), s2.st.data(), s2.tp.data(), nullptr, &s2.stats);
+            if (s2.rc) s2.err = g_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    SonicStats tot;
+    memset(&tot, 0, sizeof(tot));
+    for (int d = 0; d < nd; d++) {
+        Shard& s = sh[d];
+        if (s.rc) return set_err(s.rc, "device %d: %s", devs[d], s.err.c_str());
+        const size_t m = s.idx.size();
+        for (size_t k = 0; k < m; k++) {
+            const int64_t g = s.idx[k];
+            for (int v = 0; v < nvar; v++)
+                for (int j = 0; j < nfs; j++)
+                    out_tables[((int64_t)v * n + g) * nfs + j] = s.out[((size_t)v * m + k) * nfs + j];
+            if (out_ncycles) out_ncycles[g] = s.ncyc[k];
+            if (out_status) out_status[g] = s.st[k];
+            if (out_tpoint) out_tpoint[g] = s.tp[k];
+        }
+        if (m) {
+            tot.n_points += s.stats.n_points; tot.n_rhs += s.stats.n_rhs; tot.n_jac += s.stats.n_jac;
+            tot.n_steps += s.stats.n_steps; tot.n_cycles += s.stats.n_cycles; tot.n_launches += s.stats.n_launches;
+            tot.ms_z0 = std::max(tot.ms_z0, s.stats.ms_z0);
+            tot.ms_integrate = std::max(tot.ms_integrate, s.stats.ms_integrate);
+            tot.ms_average = std::max(tot.ms_average, s.stats.ms_average);
+        }
+    }
+    tot.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = tot;
+    return SONIC_OK;
+}
+
+int sonic_fp64_peak(int device, double* tflops) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (!tflops) return set_err(SONIC_E_ARG, "null output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double* d_out = nullptr;
+    CUDA_TRY(dalloc(&d_out, (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        sonic_dfma_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return SONIC_OK;
+}
+
+}  // extern "C"

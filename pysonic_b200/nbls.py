@@ -1,0 +1,92 @@
+# -*- coding: utf-8 -*-
+''' Neuronal bilayer sonophore: effective-variable computation on the GPU
+    (mirror of PySONIC/core/nbls.py:24-39,153-244 -- lookup-relevant part). '''
+
+import logging
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from .bls import BilayerSonophore
+from .drives import AcousticDrive
+from .neurons import PointNeuron, getPointNeuron
+
+logger = logging.getLogger('pysonic_b200')
+
+LOOKUP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lookups')
+
+
+def as_point_neuron(pneuron):
+    ''' Accept this package's descriptor, a neuron name, or any object with a `.name`
+        (e.g. a reference PySONIC PointNeuron instance). '''
+    if isinstance(pneuron, PointNeuron):
+        return pneuron
+    if isinstance(pneuron, str):
+        return getPointNeuron(pneuron)
+    if hasattr(pneuron, 'name'):
+        return getPointNeuron(pneuron.name)
+    raise ValueError(f'{pneuron} is not a valid PointNeuron instance')
+
+
+class NeuronalBilayerSonophore(BilayerSonophore):
+
+    def __init__(self, a, pneuron, embedding_depth=0.0):
+        self.pneuron = as_point_neuron(pneuron)
+        super().__init__(a, self.pneuron.Cm0, self.pneuron.Qm0, embedding_depth=embedding_depth)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.a * 1e9:.1f} nm, {self.pneuron})'
+
+    def effvars_batch(self, f, A, Q, fs, device=0):
+        ''' Effective variables for arrays of points (same radius).
+            :return: (tables[1+nrates, n, nfs], ncycles, status, tpoint, nrhs, stats) '''
+        f, A, Q = np.broadcast_arrays(np.asarray(f, float), np.asarray(A, float), np.asarray(Q, float))
+        fs = np.atleast_1d(np.asarray(fs, float))
+        ia = np.zeros(f.size, dtype=np.int32)
+        return _lib.points_run(device, [self.abi_params()], self.pneuron.neuron_id,
+                               len(self.pneuron.rates), ia, f.ravel(), A.ravel(), Q.ravel(), fs)
+
+    def computeEffVars(self, drive, fs, Qm0, Qm_overtones=None):
+        ''' Effective coefficients for one acoustic drive and charge density
+            (nbls.py:153-222; returns `(effvars_list, tcomp)` like the `@timer`-decorated
+            reference method, utils.py:408-417).
+
+            :param drive: acoustic drive object
+            :param fs: sonophore membrane coverage fraction(s)
+            :param Qm0: imposed charge density (C/m2)
+            :return: (list of one {V, rates...} dict per fs, computation time in s)
+        '''
+        if Qm_overtones is not None:
+            raise NotImplementedError('charge overtones are not supported by the GPU engine yet')
+        if not isinstance(drive, AcousticDrive) and not (hasattr(drive, 'f') and hasattr(drive, 'A')):
+            raise TypeError('Invalid "drive" parameter (must be an "AcousticDrive" object)')
+        t0 = time.perf_counter()
+        fs = np.atleast_1d(np.asarray(fs, dtype=float))
+        out, ncyc, status, _, _, _ = self.effvars_batch(drive.f, drive.A, float(Qm0), fs)
+        keys = ['V'] + self.pneuron.rates
+        effvars_list = [{k: out[i, 0, j] for i, k in enumerate(keys)} for j in range(fs.size)]
+        if status[0] & 1:
+            logger.warning('%s: periodic criterion not met -> stopped after %d cycles', self, ncyc[0])
+        return effvars_list, time.perf_counter() - t0
+
+    def getLookupFileName(self, a=None, f=None, A=None, fs=None, novertones=0):
+        ''' nbls.py:224-241 '''
+        if all(x is None for x in [a, f, A, fs]):
+            fs = 1.
+        fname = f'{self.pneuron.name}_lookups'
+        if a is not None:
+            fname += f'_{a * 1e9:.0f}nm'
+        if f is not None:
+            fname += f'_{f * 1e-3:.0f}kHz'
+        if A is not None:
+            fname += f'_{A * 1e-3:.0f}kPa'
+        if fs is not None:
+            fname += f'_fs{fs:.2f}'
+        if novertones > 0:
+            fname += f'_{novertones}overtones'
+        return f'{fname}.pkl'
+
+    def getLookupFilePath(self, *args, **kwargs):
+        return os.path.join(LOOKUP_DIR, self.getLookupFileName(*args, **kwargs))

@@ -1,0 +1,97 @@
+# -*- coding: utf-8 -*-
+''' Multi-GPU sharding of a lookup grid: one process per GPU (torch.distributed), no data-path
+    collective.  Grid points are independent, so the cost-sorted point list is dealt round-robin
+    to the ranks (every rank gets the same cost profile), each rank integrates its slab on its
+    own device, and the per-point outputs are gathered once at the end. '''
+
+import os
+
+import numpy as np
+
+
+def predicted_log_cost(a, f, A):
+    ''' Same ordering heuristic as the native work queue (sonic_b200.cu: predict_log_cost). '''
+    a, f, A = np.asarray(a, float), np.asarray(f, float), np.asarray(A, float)
+    lf, lA, la = np.log(f / 500e3), np.log1p(A / 20e3), np.log(a / 32e-9)
+    noise = ((A > 0.) & (A < 8e3)).astype(float)
+    zero = (A == 0.).astype(float)
+    return (8.142 - 0.3655 * lf + 0.9828 * lA - 0.3437 * la + 0.2427 * noise - 0.534 * zero -
+            0.0237 * lf * lA - 0.1937 * noise * lf)
+
+
+def dist_info():
+    ''' (rank, world_size, local_rank) of the current process; (0, 1, 0) outside torchrun. '''
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), int(os.environ.get('LOCAL_RANK', 0))
+    except ImportError:
+        pass
+    return 0, 1, 0
+
+
+def shard_indices(cost, rank, world_size):
+    ''' Indices of the points owned by `rank`: cost-sorted (descending), dealt round-robin. '''
+    order = np.argsort(-np.asarray(cost), kind='stable')
+    return order[rank::world_size]
+
+
+def gather_slabs(n, idx, arrays, rank, world_size):
+    ''' Gather per-point outputs from all ranks into full arrays (on every rank).
+
+        :param n: total number of points
+        :param idx: indices owned by this rank
+        :param arrays: list of arrays whose LAST-BUT-`k` axis layout is (..., len(idx), ...):
+            each array is given as (array, axis) with `axis` the point axis
+        :return: list of full arrays with `n` along the point axis
+    '''
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    # sizes differ by at most one between ranks: pad to the max
+    m = int(len(idx))
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world_size)]
+    dist.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
+    sizes = [int(s.item()) for s in sizes]
+    mmax = max(sizes)
+    idx_pad = np.full(mmax, -1, dtype=np.int64)
+    idx_pad[:m] = idx
+    all_idx = [torch.zeros(mmax, dtype=torch.int64, device=dev) for _ in range(world_size)]
+    dist.all_gather(all_idx, torch.from_numpy(idx_pad).to(dev))
+    all_idx = [t.cpu().numpy() for t in all_idx]
+    out = []
+    for arr, axis in arrays:
+        arr = np.moveaxis(np.asarray(arr), axis, 0)
+        pad = np.zeros((mmax,) + arr.shape[1:], dtype=arr.dtype)
+        pad[:m] = arr
+        t = torch.from_numpy(np.ascontiguousarray(pad)).to(dev)
+        parts = [torch.zeros_like(t) for _ in range(world_size)]
+        dist.all_gather(parts, t)
+        full = np.zeros((n,) + arr.shape[1:], dtype=arr.dtype)
+        for r in range(world_size):
+            k = sizes[r]
+            full[all_idx[r][:k]] = parts[r].cpu().numpy()[:k]
+        out.append(np.moveaxis(full, 0, axis))
+    return out
+
+
+def run_sharded(compute, n, cost, rank=None, world_size=None):
+    ''' Run `compute(idx) -> list of (array, point_axis)` on this rank's shard and gather.
+
+        `compute` receives the global indices of the points this rank owns and returns its
+        per-point outputs; the function returns the gathered full-size arrays. '''
+    r, w, _ = dist_info()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    idx = shard_indices(cost, rank, world_size)
+    outs = compute(idx)
+    if world_size == 1:
+        full = []
+        for arr, axis in outs:
+            arr = np.moveaxis(np.asarray(arr), axis, 0)
+            f = np.zeros((n,) + arr.shape[1:], dtype=arr.dtype)
+            f[idx] = arr
+            full.append(np.moveaxis(f, 0, axis))
+        return full
+    return gather_slabs(n, idx, outs, rank, world_size)

@@ -1,0 +1,192 @@
+# -*- coding: utf-8 -*-
+''' Lookup-table generation front end: `computeAStimLookup` and the `run_lookups.py` command
+    line, with the reference's signatures, grid order, table layout and file naming
+    (scripts/run_lookups.py:22-238, PySONIC/parsers.py:422-529). '''
+
+import argparse
+import logging
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+from .constants import DQ_LOOKUP
+from .lookups import Lookup
+from .nbls import NeuronalBilayerSonophore, as_point_neuron
+from .neurons import getPointNeuron
+from .parallel import dist_info, predicted_log_cost, run_sharded
+
+logger = logging.getLogger('pysonic_b200')
+
+_DESCS = {
+    'a': 'sonophore radii',
+    'f': 'US frequencies',
+    'A': 'US amplitudes',
+    'fs': 'sonophore membrane coverage fractions',
+    'Q': 'membrane charge densities',
+}
+
+
+def _is_iterable(x):
+    return isinstance(x, (list, tuple, np.ndarray))
+
+
+def _validate(refs):
+    ''' Same checks, messages and exception types as run_lookups.py:85-96. '''
+    for key, values in refs.items():
+        desc = _DESCS[key]
+        if not _is_iterable(values):
+            raise TypeError(f'Invalid {desc} (must be provided as list or numpy array)')
+        if not all(isinstance(x, float) for x in values):
+            raise TypeError(f'Invalid {desc} (must all be float typed)')
+        if len(values) == 0:
+            raise ValueError(f'Empty {key} array')
+        if key in ('a', 'f') and min(values) <= 0:
+            raise ValueError(f'Invalid {desc} (must all be strictly positive)')
+        if key in ('A', 'fs') and min(values) < 0:
+            raise ValueError(f'Invalid {desc} (must all be positive or null)')
+
+
+def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
+                       test=False, mpi=False, loglevel=logging.INFO, return_info=False):
+    ''' Effective-variable lookup tables over (a, f, A, Q, fs).
+
+        Drop-in for `computeAStimLookup` of scripts/run_lookups.py:22: same arguments (SI units:
+        m, Hz, Pa, -, C/m2), same validation, same table layout `(na, nf, nA, nQ, nfs)`, same
+        key order (`V`, rates in `pneuron.rates` order, `tcomp`).  `mpi=True` means "use every
+        available GPU": under `torchrun` the grid is sharded over the ranks (one process per
+        GPU), otherwise over the visible devices of this process.
+
+        :return: Lookup (and, if return_info, a dict with ncycles/status/stats)
+    '''
+    pneuron = as_point_neuron(pneuron)
+    refs = {'a': aref, 'f': fref, 'A': Aref, 'Q': Qref}
+    fsref = np.asarray(fsref) if _is_iterable(fsref) else fsref
+    err_span = 'cannot span {} for more than 1 {}'
+    if _is_iterable(fsref) and len(fsref) > 0 and (len(fsref) > 1 or fsref[0] != 1.):
+        for x in ['a', 'f']:
+            assert len(refs[x]) == 1, err_span.format(_DESCS['fs'], _DESCS[x])
+    refs['fs'] = fsref
+    if novertones > 0:
+        raise NotImplementedError('charge overtones are not supported by the GPU engine yet')
+    if test:
+        refs = {k: np.array([v.min(), v.max()]) if v.size > 1 else v for k, v in refs.items()}
+    _validate(refs)
+    refs = {k: np.asarray(v, dtype=np.float64) for k, v in refs.items()}
+    dims = tuple(x.size for x in refs.values())
+    na, nf, nA, nQ, nfs = dims
+    keys = ['V'] + pneuron.rates
+    nrates = len(pneuron.rates)
+    logger.log(loglevel, 'Starting lookup batch for %s neuron: %d points x %d fs', pneuron.name,
+               na * nf * nA * nQ, nfs)
+
+    bls_params = [NeuronalBilayerSonophore(float(a), pneuron).abi_params() for a in refs['a']]
+    rank, world, local_rank = dist_info()
+    t0 = time.perf_counter()
+    if world > 1:
+        # one process per GPU: shard the flattened (a > f > A > Q) list over the ranks
+        ia, fi, Ai, Qi = np.meshgrid(np.arange(na), refs['f'], refs['A'], refs['Q'], indexing='ij')
+        ia, fi, Ai, Qi = [x.ravel() for x in (ia, fi, Ai, Qi)]
+        n = ia.size
+        cost = predicted_log_cost(refs['a'][ia], fi, Ai)
+
+        def compute(idx):
+            out, ncyc, status, tpoint, nrhs, st = _lib.points_run(
+                local_rank, bls_params, pneuron.neuron_id, nrates, ia[idx].astype(np.int32),
+                fi[idx], Ai[idx], Qi[idx], refs['fs'])
+            return [(out, 1), (ncyc, 0), (status, 0), (tpoint, 0), (nrhs, 0)]
+
+        out, ncyc, status, tpoint, nrhs = run_sharded(compute, n, cost)
+        out = out.reshape((1 + nrates,) + dims)
+        ncyc, status, tpoint = [x.reshape(dims[:-1]) for x in (ncyc, status, tpoint)]
+        stats = {'n_points': n, 'n_rhs': int(nrhs.sum()), 'world_size': world}
+    else:
+        ndev = _lib.device_count()
+        mask = (1 << ndev) - 1 if (mpi and ndev > 1) else 1
+        out, ncyc, status, tpoint, stats = _lib.lookup_run(
+            bls_params, pneuron.neuron_id, nrates, refs['f'], refs['A'], refs['Q'], refs['fs'], mask)
+    wall = time.perf_counter() - t0
+    logger.log(loglevel, 'Lookup batch completed in %.3f s', wall)
+
+    tables = {k: np.ascontiguousarray(out[i]) for i, k in enumerate(keys)}
+    # per-point computation time, tiled over the fs dimension (run_lookups.py:169-172)
+    tables['tcomp'] = np.ascontiguousarray(
+        np.moveaxis(np.array([tpoint for _ in range(nfs)]), 0, -1))
+    lkp = Lookup(refs, tables)
+    if return_info:
+        return lkp, {'ncycles': ncyc, 'status': status, 'stats': stats, 'wall_s': wall}
+    return lkp
+
+
+def _parser():
+    ''' Same flags, units and defaults as MechSimParser + run_lookups.main
+        (parsers.py:422-529, run_lookups.py:180-189). '''
+    p = argparse.ArgumentParser(description='Create SONIC lookup tables on the GPU')
+    p.add_argument('-n', '--neuron', type=str, nargs='+', default=['RS'], help='Neuron name (string)')
+    p.add_argument('-a', '--radius', nargs='+', type=float, default=[16.0, 32.0, 64.0],
+                   help='Sonophore radius (nm)')
+    p.add_argument('-f', '--freq', nargs='+', type=float,
+                   default=[20., 100., 500., 1e3, 2e3, 3e3, 4e3], help='US frequency (kHz)')
+    p.add_argument('-A', '--amp', nargs='+', type=float, default=None,
+                   help='Acoustic pressure amplitude (kPa)')
+    p.add_argument('-Q', '--charge', nargs='+', type=float, default=None,
+                   help='Membrane charge density (nC/cm2)')
+    p.add_argument('--fs', nargs='+', type=float, default=[100.], help='Sonophore coverage fraction (%%)')
+    p.add_argument('--spanFs', default=False, action='store_true', help='Span Fs from 1 to 100%%')
+    p.add_argument('--mpi', default=False, action='store_true', help='Use all available GPUs')
+    p.add_argument('--test', default=False, action='store_true', help='Run test configuration')
+    p.add_argument('--novertones', type=int, default=0, help='Number of Fourier overtones')
+    p.add_argument('-v', '--verbose', default=False, action='store_true', help='Increase verbosity')
+    p.add_argument('-o', '--outputdir', type=str, default=None, help='Output directory')
+    p.add_argument('-y', '--yes', default=False, action='store_true',
+                   help='Overwrite existing lookup files without asking')
+    return p
+
+
+def main(argv=None):
+    args = _parser().parse_args(argv)
+    loglevel = logging.DEBUG if args.verbose else logging.INFO
+    logging.basicConfig(level=loglevel, format='%(asctime)s %(message)s')
+    radii = np.array(args.radius) * 1e-9
+    freqs = np.array(args.freq) * 1e3
+    if args.amp is None:
+        amps = np.insert(np.logspace(np.log10(0.1), np.log10(600), num=50), 0, 0.0) * 1e3
+    else:
+        amps = np.array(args.amp) * 1e3
+    fs = np.arange(1, 101) * 1e-2 if args.spanFs else np.array(args.fs) * 1e-2
+    for name in args.neuron:
+        pneuron = getPointNeuron(name)
+        if args.charge is None:
+            Qmin, Qmax = pneuron.Qbounds
+            charges = np.arange(Qmin, Qmax + DQ_LOOKUP, DQ_LOOKUP)
+        else:
+            charges = np.array(args.charge) * 1e-5
+        input_args = {'a': radii, 'f': freqs, 'A': amps, 'fs': fs}
+        fname_args = {k: v[0] if v.size == 1 else None for k, v in input_args.items()}
+        fname_args['novertones'] = args.novertones
+        nbls = NeuronalBilayerSonophore(32e-9, pneuron)
+        if args.outputdir is not None:
+            lookup_fpath = os.path.join(args.outputdir, nbls.getLookupFileName(**fname_args))
+        else:
+            lookup_fpath = nbls.getLookupFilePath(**fname_args)
+        if args.test:
+            fcode, fext = os.path.splitext(lookup_fpath)
+            lookup_fpath = f'{fcode}_test{fext}'
+        if os.path.isfile(lookup_fpath) and not args.yes:
+            logger.warning(f'"{lookup_fpath}" file already exists and will be overwritten. '
+                           'Continue? (y/n)')
+            if input() not in ['y', 'Y']:
+                logger.error('%s Lookup creation canceled', pneuron.name)
+                return
+        lkp = computeAStimLookup(pneuron, radii, freqs, amps, fs, charges, novertones=args.novertones,
+                                 test=args.test, mpi=args.mpi, loglevel=loglevel)
+        logger.info(f'Generated lookup: {lkp}')
+        if dist_info()[0] == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(lookup_fpath)), exist_ok=True)
+            logger.info('Saving %s neuron lookup in file: "%s"', pneuron.name, lookup_fpath)
+            lkp.toPickle(lookup_fpath)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,118 @@
+// hostsim.cpp -- CPU build of the per-lane state machine (pysonic_b200/csrc/sonic_core.h).
+//
+// TEST HARNESS ONLY: lets the CPU test-suite (`-m "not gpu"`) exercise the integrator logic
+// that the CUDA kernels run, and compare its step-by-step statistics with scipy's LSODA.
+// It is never loaded by the pysonic_b200 package.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../pysonic_b200/csrc/sonic_core.h"
+
+static SonicTables g_tab;
+static int g_tab_ready = 0;
+
+static double* g_steplog = 0;
+static long g_steplog_max = 0, g_steplog_n = 0;
+
+extern "C" {
+
+// optional per-step log: rows of 8 doubles [cycle, nst, tn, hu, h_next, nqu*10+mused, nfe, nq*10+meth]
+void hostsim_set_steplog(double* buf, long max_rows) {
+    g_steplog = buf;
+    g_steplog_max = max_rows;
+    g_steplog_n = 0;
+}
+long hostsim_steplog_rows(void) { return g_steplog_n; }
+
+// bls = {a, Delta, x0, C, nrep, nattr, Cm0, depth}
+// trace (optional, may be NULL): rows of 8 doubles per emitted sample
+//   [cycle, k, nst, nfe_in_cycle, nje_in_cycle, hu, tn, nqu*10 + mused]
+// returns number of ticks executed
+long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf, double* ngbuf,
+                   int* ncycles, unsigned* status, unsigned* stats, double* trace,
+                   long trace_rows_max, long* trace_rows) {
+    if (!g_tab_ready) {
+        sonic_fill_tables(&g_tab);
+        g_tab_ready = 1;
+    }
+    SonicBls b;
+    b.a = bls[0]; b.Delta = bls[1]; b.x0 = bls[2]; b.C = bls[3]; b.nrep = bls[4];
+    b.nattr = bls[5]; b.Cm0 = bls[6]; b.depth = bls[7];
+    SonicPoint p;
+    sonic_point_init(p, b, f, A, Q);
+    SonicSink sink;
+    sink.zbuf = zbuf; sink.ngbuf = ngbuf; sink.stride = 1;
+    SonicLane s;
+    memset(&s, 0, sizeof(s));
+    sonic_lane_init(s, p, f, sink);
+    const double period = 1.0 / f;
+    long nticks = 0, nrows = 0;
+    unsigned last_nsteps = 0;
+    int cyc0 = 0, k0 = 1;
+    unsigned nfe_base = 0, nje_base = 0;
+    while (s.phase != PH_DONE) {
+        double fv[3];
+        if (sonic_rhs(p, sonic_eval_time(s), s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
+        // snapshot of integrator statistics as they will stand when this tick emits
+        sonic_tick(s, &g_tab, sink, period, fv);
+        nticks++;
+        if (g_steplog && s.nsteps != last_nsteps && g_steplog_n < g_steplog_max) {
+            double* r = g_steplog + 8 * g_steplog_n++;
+            r[0] = s.cyc; r[1] = s.nst; r[2] = s.told; r[3] = s.hu; r[4] = s.h; r[5] = s.nqu * 10 + s.mused;
+            r[6] = s.nfe; r[7] = s.nq * 10 + s.meth;
+            last_nsteps = s.nsteps;
+        }
+        if (trace) {
+            // samples emitted by this tick: from (cyc0, k0) up to (s.cyc, s.kout) exclusive
+            while (nrows < trace_rows_max && (cyc0 < s.cyc || (cyc0 == s.cyc && k0 < s.kout))) {
+                double* r = trace + 8 * nrows++;
+                r[0] = cyc0; r[1] = k0; r[2] = s.nst; r[3] = (double)(s.nfe - nfe_base);
+                r[4] = (double)(s.nje - nje_base); r[5] = s.hu; r[6] = s.told;
+                r[7] = s.nqu * 10 + s.mused;
+                k0++;
+                if (k0 > SONIC_NOUT) {
+                    k0 = 1;
+                    cyc0++;
+                    nfe_base = s.nfe;
+                    nje_base = s.nje;
+                }
+            }
+        }
+    }
+    *ncycles = s.cyc;
+    *status = s.status;
+    stats[0] = s.nfe; stats[1] = s.nje; stats[2] = s.nsteps;
+    if (trace_rows) *trace_rows = nrows;
+    return nticks;
+}
+
+void hostsim_rhs(const double* bls, double f, double A, double Q, double t, const double* y,
+                 double* dy) {
+    SonicBls b;
+    b.a = bls[0]; b.Delta = bls[1]; b.x0 = bls[2]; b.C = bls[3]; b.nrep = bls[4];
+    b.nattr = bls[5]; b.Cm0 = bls[6]; b.depth = bls[7];
+    SonicPoint p;
+    sonic_point_init(p, b, f, A, Q);
+    sonic_rhs(p, t, y, dy);
+}
+
+double hostsim_z0(const double* bls, double f, double A, double Q) {
+    SonicBls b;
+    b.a = bls[0]; b.Delta = bls[1]; b.x0 = bls[2]; b.C = bls[3]; b.nrep = bls[4];
+    b.nattr = bls[5]; b.Cm0 = bls[6]; b.depth = bls[7];
+    SonicPoint p;
+    sonic_point_init(p, b, f, A, Q);
+    double z0 = 0.;
+    sonic_z0(p, f, &z0);
+    return z0;
+}
+
+void hostsim_tables(double* out) {
+    if (!g_tab_ready) {
+        sonic_fill_tables(&g_tab);
+        g_tab_ready = 1;
+    }
+    memcpy(out, &g_tab, sizeof(g_tab));
+}
+
+}  // extern "C"
