@@ -27,6 +27,9 @@
 #include <thread>
 #include <vector>
 
+#define SONIC_BLOCK 128
+#define SONIC_HIST_STRIDE SONIC_BLOCK   /* per-lane indexed storage interleaved across the block */
+
 #include "../../include/sonic_b200.h"
 #include "generated/neuron_rates.cuh"
 #include "sonic_core.h"
@@ -57,8 +60,8 @@ static int set_err(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------
 // device code
 // ---------------------------------------------------------------------------------------
-#define SONIC_BLOCK 128
 #define SONIC_AVG_WARPS 4
+#define SONIC_HIST_BYTES (SONIC_H_SIZE * SONIC_BLOCK * sizeof(double))
 
 struct SonicJob {
     const SonicBls* radii;
@@ -110,12 +113,14 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
     }
     __syncthreads();
 
+    extern __shared__ double hist_s[];   // [SONIC_H_SIZE][SONIC_BLOCK]
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    SonicHist H;
+    H.base = hist_s + threadIdx.x;
     SonicSink sink;
     sink.ngbuf = job.ngbuf + slot * SONIC_NPC;
     sink.zbuf = nullptr;
-    sink.stride = 1;
 
     SonicLane s;
     SonicPoint p;
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
                     job.tpoint[pt] = 0.0;
                     pt = -1;
                 } else {
-                    sonic_lane_start(s, p, f, z0, sink);
+                    sonic_lane_start(s, H, p, f, z0, sink);
                 }
             } else {
                 can_work = false;
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
         if (active) {
             double fv[3];
             if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-            sonic_tick(s, &tab, sink, period, fv);
+            sonic_tick(s, H, &tab, sink, period, fv);
             if (s.phase == PH_DONE) {
                 job.ncycles[pt] = s.cyc;
                 job.status[pt] = s.status;
@@ -479,8 +484,10 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     int blocks_per_sm = 0;
+    CUDA_TRY(cudaFuncSetAttribute(sonic_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)SONIC_HIST_BYTES));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sonic_integrate_kernel,
-                                                           SONIC_BLOCK, 0));
+                                                           SONIC_BLOCK, SONIC_HIST_BYTES));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     const long long max_blocks = (long long)prop.multiProcessorCount * blocks_per_sm;
     const long long warps_total = max_blocks * (SONIC_BLOCK / 32);
@@ -557,7 +564,7 @@ int sonic_plan_launch(SonicPlan* p) {
     CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
-    sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, 0, p->stream>>>(job);
+    sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     {
         long long blocks = (p->n + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;

@@ -28,10 +28,24 @@
 
 #if defined(__CUDACC__)
 #define SONIC_HD __host__ __device__ __forceinline__
-#define SONIC_HD_NOINLINE __host__ __device__ __noinline__
+#define SONIC_HDM __host__ __device__ __forceinline__
 #else
 #define SONIC_HD static inline
-#define SONIC_HD_NOINLINE static
+#define SONIC_HDM inline
+#endif
+
+// SONIC_EXACT_MATH (CPU harness only): keep the reference's operation forms (pow, true
+// divisions) in the right-hand side instead of the cheaper few-ulp-equivalent forms.
+#ifdef SONIC_EXACT_MATH
+#define SONIC_DIVC(x, c) ((x) / (c))
+#else
+#define SONIC_DIVC(x, c) ((x) * (1.0 / (c)))
+#endif
+// x / y where a reciprocal r of y is already at hand: the host build divides exactly.
+#if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
+#define SONIC_QUOT(x, y, r) ((x) * (r))
+#else
+#define SONIC_QUOT(x, y, r) ((x) / (y))
 #endif
 
 #define SONIC_NEQ 3
@@ -87,6 +101,10 @@ struct SonicTables {
     double cm1[12];
     double cm2[5];
     double sm1[12];
+    double lc21[5];   // log(cm2[q] / cm1[q])
+    double rk[16];    // 1 / k
+    double c21[5];    // cm2[q] / cm1[q]
+    double c12[5];    // cm1[q] / cm2[q]
 };
 
 // Per-radius constants (one entry per sonophore radius of the lookup).
@@ -100,7 +118,9 @@ struct SonicBls {
 
 // Per-point constants derived once per lane.
 struct SonicPoint {
-    double a, a2, inva2, Delta, x0, Clj, nrep, nattr, Zmin;
+    double a, a2, inva2, inva, Delta, x0, Clj, nrep, nattr, Zmin;
+    double frep, fattr;        // fractional parts nrep - krep, nattr - kattr
+    int krep, kattr;           // nearest integers of the two Lennard-Jones exponents
     double V0, c_vol;          // V = V0 * (1 + Z * c_vol * (3 + Z^2 * inva2)), c_vol = 1/(3 Delta)
     double kAtot;              // kA + kA_tissue (N/m)
     double pel0;               // Q^2 / (2 eps0 epsR)
@@ -113,11 +133,18 @@ SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, doubl
     p.a = b.a;
     p.a2 = b.a * b.a;
     p.inva2 = 1.0 / p.a2;
+    p.inva = 1.0 / b.a;
     p.Delta = b.Delta;
     p.x0 = b.x0;
     p.Clj = b.C;
     p.nrep = b.nrep;
     p.nattr = b.nattr;
+    p.krep = (int)rint(b.nrep);
+    p.kattr = (int)rint(b.nattr);
+    if (p.krep < 0 || p.krep > 8) p.krep = 0;
+    if (p.kattr < 0 || p.kattr > 8) p.kattr = 0;
+    p.frep = b.nrep - p.krep;
+    p.fattr = b.nattr - p.kattr;
     p.Zmin = SONIC_REL_ZMIN * b.Delta;
     p.V0 = SONIC_PI * b.Delta * p.a2;                   // bls.py:136
     p.c_vol = 1.0 / (3.0 * b.Delta);
@@ -128,21 +155,94 @@ SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, doubl
     p.ng0 = SONIC_P0 * p.V0 / (SONIC_RG * SONIC_T);     // bls.py:137,529-536
 }
 
-// Lennard-Jones intermolecular pressure (bls.py:29-41,472-480).
-SONIC_HD double sonic_pm(const SonicPoint& p, double Z) {
-    const double x = p.x0 / (2.0 * Z + p.Delta);
-#ifdef SONIC_FAST_POW
-    const double lx = log(x);
-    return p.Clj * (exp(p.nrep * lx) - exp(p.nattr * lx));
+// Reciprocal: hardware seed + Newton refinement on the device (<= 1 ulp), exact division on the
+// host build.
+SONIC_HD double sonic_rcp(double x) {
+#if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 #else
-    return p.Clj * (pow(x, p.nrep) - pow(x, p.nattr));
+    return 1.0 / x;
 #endif
+}
+
+// Quotient: x * rcp(y) on the device (<= 2 ulp), IEEE division on the host build.
+SONIC_HD double sonic_div(double x, double y) {
+#if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
+    return x * sonic_rcp(y);
+#else
+    return x / y;
+#endif
+}
+
+// x^k for a small non-negative integer k (binary powering, k <= 8).
+SONIC_HD double sonic_ipow(double x, int k) {
+    if (k == 4) {
+        const double x2 = x * x;
+        return x2 * x2;
+    }
+    if (k == 1) return x;
+    double r = (k & 1) ? x : 1.0;
+    const double x2 = x * x;
+    if (k & 2) r *= x2;
+    const double x4 = x2 * x2;
+    if (k & 4) r *= x4;
+    if (k & 8) r *= x4 * x4;
+    return r;
+}
+
+// d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).
+SONIC_HD double sonic_powr(double d, double ex) {
+#if defined(__CUDA_ARCH__)
+    return exp(ex * log(d));
+#else
+    return pow(d, ex);
+#endif
+}
+
+// (d * c)^ex where log(d) may already be known (NaN = not yet) and lc = log(c) is tabulated:
+// on the device the logarithm of the local error estimate is computed once per step and shared
+// by every step-size candidate that is derived from it.
+SONIC_HD double sonic_powr_scaled(double d, double c, double lc, double ex, double* ld) {
+#if defined(__CUDA_ARCH__)
+    if (*ld != *ld) *ld = log(d);
+    return exp(ex * (*ld + lc));
+#else
+    (void)lc; (void)ld;
+    return pow(d * c, ex);
+#endif
+}
+
+// Lennard-Jones intermolecular pressure (bls.py:29-41,472-480).
+// x^n is evaluated as x^k * exp((n - k) log x) with k = rint(n): the two powers share one
+// logarithm and the exponential only carries the small fractional part, which keeps the result
+// within a few ulp of a correctly rounded pow at a third of its cost.
+SONIC_HD double sonic_pm(const SonicPoint& p, double Z) {
+#ifdef SONIC_EXACT_MATH
+    const double xe = p.x0 / (2.0 * Z + p.Delta);
+    return p.Clj * (pow(xe, p.nrep) - pow(xe, p.nattr));
+#endif
+    const double x = p.x0 * sonic_rcp(2.0 * Z + p.Delta);
+    const double lx = log(x);
+    const double prep = sonic_ipow(x, p.krep) * exp(p.frep * lx);
+    const double pattr = sonic_ipow(x, p.kattr) * exp(p.fattr * lx);
+    return p.Clj * (prep - pattr);
 }
 
 // Gas pressure in the cavity (bls.py:311-319,518-526).
 SONIC_HD double sonic_pg(const SonicPoint& p, double Z, double ng) {
     const double V = p.V0 * (1.0 + Z * p.c_vol * (3.0 + Z * Z * p.inva2));
+#ifdef SONIC_EXACT_MATH
     return ng * (SONIC_RG * SONIC_T) / V;
+#else
+    return ng * (SONIC_RG * SONIC_T) * sonic_rcp(V);
+#endif
 }
 
 // Right-hand side (bls.py:681-718).  Returns true if the Zmin clamp was applied.
@@ -156,7 +256,7 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
         clamped = true;
     }
     const double s2 = p.a2 + Z * Z;                     // S / pi
-    const double inv_s2 = 1.0 / s2;
+    const double inv_s2 = sonic_rcp(s2);
     const double invR = 2.0 * Z * inv_s2;               // 1 / curvature radius (0 at Z = 0)
     const double ainvR = fabs(invR);
     const double Pg = sonic_pg(p, Z, ng);
@@ -164,20 +264,29 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     const double Pac = p.A * sin(p.omega * t - SONIC_PI);             // drives.py:303-304
     const double Pv = -12.0 * U * SONIC_DELTA0 * SONIC_MUS * (invR * invR)
                       - 4.0 * U * SONIC_MUL * ainvR;                  // bls.py:613-631
+#ifdef SONIC_EXACT_MATH
     const double zr = Z / p.a;
+#else
+    const double zr = Z * p.inva;
+#endif
     const double PE = -(p.kAtot * (zr * zr)) * invR;                  // bls.py:575-611
     const double Pel = -(p.a2 * inv_s2) * p.pel0;                     // bls.py:482-491
     const double Ptot = Pm + Pg - SONIC_P0 - Pac + PE + Pv + Pel;
-    dy[0] = Ptot * ainvR / SONIC_RHOL - 1.5 * (U * U) * invR;         // bls.py:633-655
+    dy[0] = SONIC_DIVC(Ptot * ainvR, SONIC_RHOL) - 1.5 * (U * U) * invR;   // bls.py:633-655
     dy[1] = U;
-    dy[2] = 2.0 * (SONIC_PI * s2) * SONIC_DGL * (SONIC_C0 - Pg / SONIC_KH) / SONIC_XI;  // :508-516
+    dy[2] = SONIC_DIVC(2.0 * (SONIC_PI * s2) * SONIC_DGL * (SONIC_C0 - SONIC_DIVC(Pg, SONIC_KH)),
+                       SONIC_XI);                                    // bls.py:508-516
     return clamped;
 }
 
 // Quasi-static net pressure (bls.py:538-553).
 SONIC_HD double sonic_ptot_qs(const SonicPoint& p, double Z, double ng, double Pac) {
     const double s2 = p.a2 + Z * Z;
+#ifdef SONIC_EXACT_MATH
     return sonic_pm(p, Z) + sonic_pg(p, Z, ng) - SONIC_P0 - Pac - (p.a2 / s2) * p.pel0;
+#else
+    return sonic_pm(p, Z) + sonic_pg(p, Z, ng) - SONIC_P0 - Pac - (p.a2 * sonic_rcp(s2)) * p.pel0;
+#endif
 }
 
 // Initial deflection: root of the quasi-static pressure on (Zmin, a) for
@@ -260,200 +369,281 @@ enum SonicPhase : int {
     PH_DONE = 5
 };
 
+// Indexed per-lane storage ("history"): everything that is addressed with a run-time index
+// (Nordsieck columns, iteration matrix) or touched rarely.  On the device it lives in shared
+// memory, element k of lane t at base[k * SONIC_HIST_STRIDE] with base = block_array + t, so
+// that any per-lane index pattern is bank-conflict free; in the CPU harness it is a plain
+// array (stride 1).  Everything else of the lane is scalar and stays in registers.
+#ifndef SONIC_HIST_STRIDE
+#define SONIC_HIST_STRIDE 1
+#endif
+#define SONIC_H_YH 0       /* 39: yh[j][i] at 3 j + i, yh[j] = h^j y^(j) / j! */
+#define SONIC_H_WM 39      /* 9: LU factors of P = I - h el0 J, column-major */
+#define SONIC_H_SSQZ 48    /* convergence accumulators of the running cycle */
+#define SONIC_H_SSQN 49
+#define SONIC_H_MINZ 50
+#define SONIC_H_MAXZ 51
+#define SONIC_H_MINN 52
+#define SONIC_H_MAXN 53
+#define SONIC_H_SIZE 54
+
+struct SonicHist {
+    double* base;
+    SONIC_HDM double& at(int k) const { return base[k * SONIC_HIST_STRIDE]; }
+    SONIC_HDM double& yh(int j, int i) const { return base[(3 * j + i) * SONIC_HIST_STRIDE]; }
+    SONIC_HDM double& wm(int k) const { return base[(SONIC_H_WM + k) * SONIC_HIST_STRIDE]; }
+};
+
 struct SonicLane {
-    // ---- integrator (LSODA) ----
-    double yh[SONIC_NYH][SONIC_NEQ];   // Nordsieck history, yh[j] = h^j y^(j) / j!
-    double wm[9];                      // LU factors of P = I - h el0 J (row-major)
-    double ewt[3], savf[3], acor[3], y[3];
-    double h, hu, tn, told, rc, el0, crate, rmax, conit;
+    // ---- integrator ----
+    double y[3];                       // evaluation point of the next tick
+    double ewt[3], savf[3], acor[3];
+    double h, tn, told, rc, el0, crate, rmax, conit;
     double pdest, pdlast, pdnorm, dsm, pnorm, del, delp, rate;
     double yj_save, jac_r0;
-    int ipvt[3];
-    int nq, l, meth, miter, mused, nqu, ialth, ipup, icount, irflag, jcur, kflag, m, ncf;
-    int nst, nslp, nslast, jstart, lmax, tab_meth, jcol, ierpj;
+    int nq, meth, miter, mused, ialth, ipup, icount, irflag, jcur, kflag, m, ncf;
+    int nst, nslp, nslast, jstart, tab_meth, jcol, ierpj, ipvt;
     int phase;
     // ---- output / cycle bookkeeping ----
     double t0, tstop, tstep, tout;
-    double ssq_z, ssq_ng, min_z, max_z, min_ng, max_ng;
+    double prev_z, prev_ng;            // previous-cycle samples at index kout (prefetched)
     int cyc, kout;
     unsigned status;
     // ---- statistics ----
     unsigned nfe, nje, nsteps;
+#ifdef SONIC_TRACE
+    double hu;
+    int nqu;
+#endif
 };
 
-SONIC_HD double sonic_mnorm(const double v[3], const double w[3]) {
+SONIC_HD double sonic_mnorm3(double v0, double v1, double v2, const double w[3]) {
     double vm = 0.0;
-    vm = fmax(vm, fabs(v[0]) * w[0]);
-    vm = fmax(vm, fabs(v[1]) * w[1]);
-    vm = fmax(vm, fabs(v[2]) * w[2]);
+    vm = fmax(vm, fabs(v0) * w[0]);
+    vm = fmax(vm, fabs(v1) * w[1]);
+    vm = fmax(vm, fabs(v2) * w[2]);
     return vm;
 }
 
-SONIC_HD void sonic_ewset(SonicLane& s) {
-    for (int i = 0; i < 3; i++) s.ewt[i] = 1.0 / (SONIC_RTOL * fabs(s.yh[0][i]) + SONIC_ATOL);
+SONIC_HD double sonic_mnorm(const double v[3], const double w[3]) {
+    return sonic_mnorm3(v[0], v[1], v[2], w);
+}
+
+SONIC_HD double sonic_mnorm_col(const SonicHist& H, int j, const double w[3]) {
+    return sonic_mnorm3(H.yh(j, 0), H.yh(j, 1), H.yh(j, 2), w);
+}
+
+SONIC_HD void sonic_ewset(SonicLane& s, const SonicHist& H) {
+    s.ewt[0] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 0)) + SONIC_ATOL);
+    s.ewt[1] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 1)) + SONIC_ATOL);
+    s.ewt[2] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 2)) + SONIC_ATOL);
 }
 
 // coefficient accessors: l-vector of the current order in the currently loaded table
 #define SONIC_EL(s, T, j) ((T)->elco[(s).tab_meth - 1][(s).nq - 1][(j)])
 #define SONIC_TESCO(s, T, k) ((T)->tesco[(s).tab_meth - 1][(s).nq - 1][(k)])
+#define SONIC_LMAX(s) ((s).tab_meth == 2 ? SONIC_MXORDS + 1 : SONIC_MXORDN + 1)
 
 // Reset the order-dependent constants (order nq of the loaded family).
 SONIC_HD void sonic_set_order(SonicLane& s, const SonicTables* T) {
     const double el1 = SONIC_EL(s, T, 0);
-    s.rc = s.rc * el1 / s.el0;
+    s.rc = sonic_div(s.rc * el1, s.el0);
     s.el0 = el1;
-    s.conit = 0.5 / (s.nq + 2);
+    s.conit = 0.5 * T->rk[s.nq + 2];
 }
 
 // Multiply yh by the Pascal triangle (prediction) or its inverse (retraction).
-SONIC_HD void sonic_pascal(SonicLane& s, int sign) {
-    // For jb = 1..nq the sweep updates columns nq-jb .. nq-1 (0-based) in ascending order.
+// For jb = 1..nq the sweep updates columns nq-jb .. nq-1 (0-based) in ascending order.
+SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double sign) {
+    const int nq = s.nq;
+    if (nq <= 5) {
+        // Low orders (every BDF order): columns held in registers, top-aligned
+        // (c[k] = column nq - k), so that sweep jb is "c[k] += c[k-1] for k = jb..1" whatever
+        // the order; the same additions in the same order as the generic loop below.
+        double c[6][3];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int j = nq - k;
+            const bool v = j >= 0;
+            c[k][0] = v ? H.yh(v ? j : 0, 0) : 0.0;
+            c[k][1] = v ? H.yh(v ? j : 0, 1) : 0.0;
+            c[k][2] = v ? H.yh(v ? j : 0, 2) : 0.0;
+        }
+#pragma unroll
+        for (int jb = 1; jb <= 5; jb++) {
+            if (jb <= nq) {
+#pragma unroll
+                for (int k = jb; k >= 1; k--) {
+                    c[k][0] += sign * c[k - 1][0];
+                    c[k][1] += sign * c[k - 1][1];
+                    c[k][2] += sign * c[k - 1][2];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 1; k < 6; k++) {
+            const int j = nq - k;
+            if (j >= 0) {
+                H.yh(j, 0) = c[k][0];
+                H.yh(j, 1) = c[k][1];
+                H.yh(j, 2) = c[k][2];
+            }
+        }
+        return;
+    }
     for (int jb = 1; jb <= s.nq; jb++) {
         for (int j = s.nq - jb; j < s.nq; j++) {
-            if (sign > 0) {
-                s.yh[j][0] += s.yh[j + 1][0];
-                s.yh[j][1] += s.yh[j + 1][1];
-                s.yh[j][2] += s.yh[j + 1][2];
-            } else {
-                s.yh[j][0] -= s.yh[j + 1][0];
-                s.yh[j][1] -= s.yh[j + 1][1];
-                s.yh[j][2] -= s.yh[j + 1][2];
-            }
+            H.yh(j, 0) += sign * H.yh(j + 1, 0);
+            H.yh(j, 1) += sign * H.yh(j + 1, 1);
+            H.yh(j, 2) += sign * H.yh(j + 1, 2);
         }
     }
 }
 
 // Apply a step-size ratio: bound it, restrict by the Adams stability region, rescale history.
-SONIC_HD void sonic_rescale(SonicLane& s, const SonicTables* T, double rh) {
+SONIC_HD void sonic_rescale(SonicLane& s, const SonicHist& H, const SonicTables* T, double rh) {
     rh = fmin(rh, s.rmax);
     if (s.meth == 1) {
         s.irflag = 0;
         const double pdh = fmax(fabs(s.h) * s.pdlast, 0.000001);
         if (rh * pdh * 1.00001 >= T->sm1[s.nq - 1]) {
-            rh = T->sm1[s.nq - 1] / pdh;
+            rh = sonic_div(T->sm1[s.nq - 1], pdh);
             s.irflag = 1;
         }
     }
     double r = 1.0;
-    for (int j = 1; j < s.l; j++) {
+    for (int j = 1; j <= s.nq; j++) {
         r *= rh;
-        s.yh[j][0] *= r;
-        s.yh[j][1] *= r;
-        s.yh[j][2] *= r;
+        H.yh(j, 0) *= r;
+        H.yh(j, 1) *= r;
+        H.yh(j, 2) *= r;
     }
     s.h *= rh;
     s.rc *= rh;
-    s.ialth = s.l;
+    s.ialth = s.nq + 1;
 }
 
 // Prediction: advance tn, apply Pascal triangle, set the evaluation point.
-SONIC_HD void sonic_predict(SonicLane& s) {
+SONIC_HD void sonic_predict(SonicLane& s, const SonicHist& H) {
     if (fabs(s.rc - 1.0) > 0.3) s.ipup = s.miter;
     if (s.nst >= s.nslp + 20) s.ipup = s.miter;
     s.tn += s.h;
-    sonic_pascal(s, +1);
-    s.pnorm = sonic_mnorm(s.yh[0], s.ewt);
+    sonic_pascal(s, H, 1.0);
+    s.y[0] = H.yh(0, 0);
+    s.y[1] = H.yh(0, 1);
+    s.y[2] = H.yh(0, 2);
+    s.pnorm = sonic_mnorm(s.y, s.ewt);
     s.m = 0;
     s.rate = 0.0;
     s.del = 0.0;
-    s.y[0] = s.yh[0][0];
-    s.y[1] = s.yh[0][1];
-    s.y[2] = s.yh[0][2];
     s.phase = PH_CORR_FIRST;
 }
 
-// 3x3 LU with partial pivoting (column-major semantics of the reference solver: first
-// maximal pivot, multipliers stored negated) and the matching solve.
-SONIC_HD int sonic_lu3(double a[9], int ipvt[3]) {
-    // a[i + 3*j] = A(i, j)
+// 3x3 LU with partial pivoting on the iteration matrix held in the history storage
+// (column-major, first maximal pivot, multipliers stored negated) and the matching solve.
+// The two pivot rows are packed in s.ipvt (2 bits each).
+SONIC_HD int sonic_lu3(const SonicHist& H, int* ipvt_packed) {
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[k] = H.wm(k);
     int info = 0;
+    int piv = 0;
+#pragma unroll
     for (int k = 0; k < 2; k++) {
-        int lmax_ = k;
+        int lp = k;
         double dmax = fabs(a[k + 3 * k]);
+#pragma unroll
         for (int i = k + 1; i < 3; i++)
             if (fabs(a[i + 3 * k]) > dmax) {
                 dmax = fabs(a[i + 3 * k]);
-                lmax_ = i;
+                lp = i;
             }
-        ipvt[k] = lmax_;
-        if (a[lmax_ + 3 * k] == 0.0) {
+        piv |= lp << (2 * k);
+        // row exchange of column k, k+1.. performed with selects (no dynamic register index)
+        double akk = a[k + 3 * k];
+#pragma unroll
+        for (int i = k + 1; i < 3; i++)
+            if (lp == i) {
+                akk = a[i + 3 * k];
+                a[i + 3 * k] = a[k + 3 * k];
+                a[k + 3 * k] = akk;
+            }
+        if (akk == 0.0) {
             info = k + 1;
             continue;
         }
-        if (lmax_ != k) {
-            const double t = a[lmax_ + 3 * k];
-            a[lmax_ + 3 * k] = a[k + 3 * k];
-            a[k + 3 * k] = t;
-        }
-        const double tinv = -1.0 / a[k + 3 * k];
+        const double tinv = -sonic_rcp(akk);
+#pragma unroll
         for (int i = k + 1; i < 3; i++) a[i + 3 * k] *= tinv;
+#pragma unroll
         for (int j = k + 1; j < 3; j++) {
-            double t = a[lmax_ + 3 * j];
-            if (lmax_ != k) {
-                a[lmax_ + 3 * j] = a[k + 3 * j];
-                a[k + 3 * j] = t;
-            }
+            double t = a[k + 3 * j];
+#pragma unroll
+            for (int i = k + 1; i < 3; i++)
+                if (lp == i) {
+                    t = a[i + 3 * j];
+                    a[i + 3 * j] = a[k + 3 * j];
+                    a[k + 3 * j] = t;
+                }
+#pragma unroll
             for (int i = k + 1; i < 3; i++) a[i + 3 * j] += t * a[i + 3 * k];
         }
     }
-    ipvt[2] = 2;
     if (a[8] == 0.0) info = 3;
+#pragma unroll
+    for (int k = 0; k < 9; k++) H.wm(k) = a[k];
+    *ipvt_packed = piv;
     return info;
 }
 
-SONIC_HD void sonic_lusolve3(const double a[9], const int ipvt[3], double b[3]) {
+SONIC_HD void sonic_lusolve3(const SonicHist& H, int ipvt_packed, double b[3]) {
+    double a[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) a[k] = H.wm(k);
+#pragma unroll
     for (int k = 0; k < 2; k++) {
-        const int lp = ipvt[k];
-        const double t = b[lp];
-        if (lp != k) {
-            b[lp] = b[k];
-            b[k] = t;
-        }
+        const int lp = (ipvt_packed >> (2 * k)) & 3;
+        double t = b[k];
+#pragma unroll
+        for (int i = k + 1; i < 3; i++)
+            if (lp == i) {
+                t = b[i];
+                b[i] = b[k];
+                b[k] = t;
+            }
+#pragma unroll
         for (int i = k + 1; i < 3; i++) b[i] += t * a[i + 3 * k];
     }
+#pragma unroll
     for (int k = 2; k >= 0; k--) {
-        b[k] /= a[k + 3 * k];
+        b[k] = sonic_div(b[k], a[k + 3 * k]);
         const double t = -b[k];
+#pragma unroll
         for (int i = 0; i < k; i++) b[i] += t * a[i + 3 * k];
     }
 }
 
 // Interpolate the solution at time t from the Nordsieck history (k = 0 derivative).
-SONIC_HD void sonic_interp(const SonicLane& s, double t, double out[3]) {
-    const double sfrac = (t - s.tn) / s.h;
-    out[0] = s.yh[s.l - 1][0];
-    out[1] = s.yh[s.l - 1][1];
-    out[2] = s.yh[s.l - 1][2];
+SONIC_HD void sonic_interp(const SonicLane& s, const SonicHist& H, double t, double out[3]) {
+    const double sfrac = sonic_div(t - s.tn, s.h);
+    out[0] = H.yh(s.nq, 0);
+    out[1] = H.yh(s.nq, 1);
+    out[2] = H.yh(s.nq, 2);
     for (int j = s.nq - 1; j >= 0; j--) {
-        out[0] = s.yh[j][0] + sfrac * out[0];
-        out[1] = s.yh[j][1] + sfrac * out[1];
-        out[2] = s.yh[j][2] + sfrac * out[2];
+        out[0] = H.yh(j, 0) + sfrac * out[0];
+        out[1] = H.yh(j, 1) + sfrac * out[1];
+        out[2] = H.yh(j, 2) + sfrac * out[2];
     }
 }
 
-// Start a fresh problem at (t0, y0) for one acoustic cycle of period T (odeint call).
-SONIC_HD void sonic_cycle_begin(SonicLane& s, double t0, double T, const double y0[3]) {
-    s.t0 = t0;
-    s.tstop = t0 + T;                                   // solvers.py:334
-    s.tstep = (s.tstop - s.t0) / (double)SONIC_NOUT;    // numpy.linspace step
-    s.kout = 1;
-    // tout_k = k * step + start, two separately rounded operations as numpy does
-#if defined(__CUDA_ARCH__)
-    s.tout = __dadd_rn(__dmul_rn(1.0, s.tstep), s.t0);
-#else
-    s.tout = 1.0 * s.tstep + s.t0;
-#endif
-    s.ssq_z = s.ssq_ng = 0.0;
-    s.min_z = s.min_ng = INFINITY;
-    s.max_z = s.max_ng = -INFINITY;
-    s.y[0] = y0[0];
-    s.y[1] = y0[1];
-    s.y[2] = y0[2];
-    s.tn = t0;
-    s.phase = PH_INIT;
-}
+struct SonicSink {
+    // where the lane stores its per-cycle samples
+    double* zbuf;    // [1000]: zbuf[0] = Z at the start of the current cycle, zbuf[k] sample k
+    double* ngbuf;   // [1000]
+};
 
 SONIC_HD double sonic_tout_at(const SonicLane& s, int k) {
+    // numpy.linspace: k * step + start with two separately rounded operations, last = stop
     if (k >= SONIC_NOUT) return s.tstop;
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(__dmul_rn((double)k, s.tstep), s.t0);
@@ -463,17 +653,30 @@ SONIC_HD double sonic_tout_at(const SonicLane& s, int k) {
 #endif
 }
 
-// Evaluation point of the next tick.
-SONIC_HD double sonic_eval_time(const SonicLane& s) { return s.tn; }
-
-struct SonicSink {
-    // where the lane stores its per-cycle samples; stride in doubles between samples
-    double* zbuf;    // [1000]: zbuf[0] = Z at the start of the current cycle, zbuf[k] sample k
-    double* ngbuf;   // [1000]
-    long stride;
-};
-
-// --- pieces of the step controller ----------------------------------------------------------
+// Start a fresh problem at (t0, y0) for one acoustic cycle of period T (one odeint call).
+SONIC_HD void sonic_cycle_begin(SonicLane& s, const SonicHist& H, const SonicSink& sink, double t0,
+                                double T, const double y0[3]) {
+    s.t0 = t0;
+    s.tstop = t0 + T;                                   // solvers.py:334
+    s.tstep = (s.tstop - s.t0) / (double)SONIC_NOUT;    // numpy.linspace step
+    s.kout = 1;
+    s.tout = sonic_tout_at(s, 1);
+    H.at(SONIC_H_SSQZ) = 0.0;
+    H.at(SONIC_H_SSQN) = 0.0;
+    H.at(SONIC_H_MINZ) = INFINITY;
+    H.at(SONIC_H_MINN) = INFINITY;
+    H.at(SONIC_H_MAXZ) = -INFINITY;
+    H.at(SONIC_H_MAXN) = -INFINITY;
+    if (s.cyc >= 1) {
+        s.prev_z = sink.zbuf[1];
+        s.prev_ng = sink.ngbuf[1];
+    }
+    s.y[0] = y0[0];
+    s.y[1] = y0[1];
+    s.y[2] = y0[2];
+    s.tn = t0;
+    s.phase = PH_INIT;
+}
 
 // Fatal integrator condition: stop the lane.
 SONIC_HD void sonic_fail(SonicLane& s, unsigned bit) {
@@ -481,23 +684,42 @@ SONIC_HD void sonic_fail(SonicLane& s, unsigned bit) {
     s.phase = PH_DONE;
 }
 
-// Choose the next order/step after a success (ialth == 0) or an error-test failure.
-// Returns: 0 = accepted and finished (step OK, no redo), 1 = must redo the step (predict again)
-SONIC_HD int sonic_select(SonicLane& s, const SonicTables* T, double rhup, int iredo) {
-    const double exsm = 1.0 / s.l;
-    double rhsm = 1.0 / (1.2 * pow(s.dsm, exsm) + 0.0000012);
+// Choose the next order/step after a success (ialth == 0, iredo = 0) or an error-test failure
+// (iredo = 2).  Returns true if the step must be redone (predict again).
+// Step-size candidate at the current order from the local error estimate dsm:
+// 1 / (1.2 dsm^(1/l) + 1.2e-6).  Needed by both the method-switch test and the order
+// selection of the same step, so it is computed once (NaN = not yet) together with log(dsm).
+struct SonicStepCtx {
+    double rhsm0;
+    double lds;
+};
+
+SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepCtx* c) {
+    if (c->rhsm0 != c->rhsm0) {
+        const double exsm = T->rk[s.nq + 1];
+        c->rhsm0 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, 1.0, 0.0, exsm, &c->lds) + 0.0000012);
+    }
+    return c->rhsm0;
+}
+
+SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* T, double rhup,
+                           int iredo, SonicStepCtx* ctx) {
+    const int l = s.nq + 1;
+    const int lmax = SONIC_LMAX(s);
+    double rhsm = sonic_rhsm0(s, T, ctx);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = sonic_mnorm(s.yh[s.l - 1], s.ewt) / SONIC_TESCO(s, T, 0);
-        const double exdn = 1.0 / s.nq;
-        rhdn = 1.0 / (1.3 * pow(ddn, exdn) + 0.0000013);
+        const double ddn = sonic_div(sonic_mnorm_col(H, s.nq, s.ewt), SONIC_TESCO(s, T, 0));
+        const double exdn = T->rk[s.nq];
+        rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn) + 0.0000013);
     }
     double pdh = 0.0;
     if (s.meth == 1) {
         pdh = fmax(fabs(s.h) * s.pdlast, 0.000001);
-        if (s.l < s.lmax) rhup = fmin(rhup, T->sm1[s.l - 1] / pdh);
-        rhsm = fmin(rhsm, T->sm1[s.nq - 1] / pdh);
-        if (s.nq > 1) rhdn = fmin(rhdn, T->sm1[s.nq - 2] / pdh);
+        const double rpdh = sonic_rcp(pdh);
+        if (l < lmax) rhup = fmin(rhup, SONIC_QUOT(T->sm1[l - 1], pdh, rpdh));
+        rhsm = fmin(rhsm, SONIC_QUOT(T->sm1[s.nq - 1], pdh, rpdh));
+        if (s.nq > 1) rhdn = fmin(rhdn, SONIC_QUOT(T->sm1[s.nq - 2], pdh, rpdh));
         s.pdest = 0.0;
     }
     int newq;
@@ -511,188 +733,64 @@ SONIC_HD int sonic_select(SonicLane& s, const SonicTables* T, double rhup, int i
             newq = s.nq;
             rh = rhsm;
         }
-    } else {
-        if (rhup > rhdn) {
-            // order increase
-            newq = s.l;
-            rh = rhup;
-            if (rh < 1.1) {
-                s.ialth = 3;
-                return 0;
-            }
-            const double r = SONIC_EL(s, T, s.l - 1) / s.l;
-            s.yh[newq][0] = s.acor[0] * r;
-            s.yh[newq][1] = s.acor[1] * r;
-            s.yh[newq][2] = s.acor[2] * r;
-            s.nq = newq;
-            s.l = s.nq + 1;
-            sonic_set_order(s, T);
-            sonic_rescale(s, T, rh);
-            if (iredo == 0) s.rmax = 10.0;
-            return iredo != 0;
+    } else if (rhup > rhdn) {
+        // order increase: one more scaled derivative is appended
+        rh = rhup;
+        if (rh < 1.1) {
+            s.ialth = 3;
+            return false;
         }
+        const double r = SONIC_QUOT(SONIC_EL(s, T, l - 1), (double)l, T->rk[l]);
+        H.yh(l, 0) = s.acor[0] * r;
+        H.yh(l, 1) = s.acor[1] * r;
+        H.yh(l, 2) = s.acor[2] * r;
+        s.nq = l;
+        sonic_set_order(s, T);
+        sonic_rescale(s, H, T, rh);
+        if (iredo == 0) s.rmax = 10.0;
+        return iredo != 0;
+    } else {
         newq = s.nq - 1;
         rh = rhdn;
         if (s.kflag < 0 && rh > 1.0) rh = 1.0;
     }
-    // 10 percent test, bypassed when Adams step is stability-limited
+    // 10 percent test, bypassed when the Adams step is stability-limited
     bool bypass = false;
     if (s.meth == 1 && rh * pdh * 1.00001 >= T->sm1[newq - 1]) bypass = true;
     if (!bypass && s.kflag == 0 && rh < 1.1) {
         s.ialth = 3;
-        return 0;
+        return false;
     }
     if (s.kflag <= -2) rh = fmin(rh, 0.2);
     if (newq != s.nq) {
         s.nq = newq;
-        s.l = s.nq + 1;
         sonic_set_order(s, T);
     }
-    sonic_rescale(s, T, rh);
+    sonic_rescale(s, H, T, rh);
     if (iredo == 0) s.rmax = 10.0;
     return iredo != 0;
 }
 
-// Preliminaries before attempting a step (driver level + step entry).
-// Returns false if the lane stopped.
-SONIC_HD bool sonic_step_begin(SonicLane& s, const SonicTables* T, bool first) {
-    if (!first) {
-        if (s.nst - s.nslast >= SONIC_MXSTEP) {
-            sonic_fail(s, SONIC_ST_MXSTEP);
-            return false;
-        }
-        sonic_ewset(s);
-    }
-    const double tolsf = SONIC_UROUND * sonic_mnorm(s.yh[0], s.ewt);
-    if (tolsf > 1.0) {
-        sonic_fail(s, SONIC_ST_TOLSF);
-        return false;
-    }
-    // step entry
-    s.kflag = 0;
-    s.told = s.tn;
-    s.ncf = 0;
-    s.ierpj = 0;
-    s.jcur = 0;
-    s.delp = 0.0;
-    if (s.jstart == 0) {
-        s.lmax = SONIC_MXORDN + 1;
-        s.nq = 1;
-        s.l = 2;
-        s.ialth = 2;
-        s.rmax = 10000.0;
-        s.rc = 0.0;
-        s.el0 = 1.0;
-        s.crate = 0.7;
-        s.nslp = 0;
-        s.ipup = s.miter;
-        s.icount = 20;
-        s.irflag = 0;
-        s.pdest = 0.0;
-        s.pdlast = 0.0;
-        s.tab_meth = 1;
-        sonic_set_order(s, T);
-    } else if (s.jstart == -1) {
-        s.ipup = s.miter;
-        s.lmax = (s.meth == 2 ? SONIC_MXORDS : SONIC_MXORDN) + 1;
-        if (s.ialth == 1) s.ialth = 2;
-        if (s.meth != s.mused) {
-            s.tab_meth = s.meth;
-            s.ialth = s.l;
-            sonic_set_order(s, T);
-        }
-    }
-    s.jstart = 1;
-    sonic_predict(s);
-    return true;
-}
-
-// Output handling after a successful step: emit every sample reached, handle the end of the
-// cycle (convergence test, next cycle or stop).  Returns true if the lane continues stepping
-// within the same problem, false if it either finished or started a new problem (phase set).
-SONIC_HD bool sonic_emit(SonicLane& s, const SonicSink& sink, double period) {
-    while ((s.tn - s.tout) * s.h >= 0.0) {
-        double yo[3];
-        sonic_interp(s, s.tout, yo);
-        const long idx = (long)s.kout * sink.stride;
-        if (s.cyc >= 1) {
-            const double dz = yo[1] - sink.zbuf[idx];
-            const double dn = yo[2] - sink.ngbuf[idx];
-            s.ssq_z += dz * dz;
-            s.ssq_ng += dn * dn;
-            s.min_z = fmin(s.min_z, yo[1]);
-            s.max_z = fmax(s.max_z, yo[1]);
-            s.min_ng = fmin(s.min_ng, yo[2]);
-            s.max_ng = fmax(s.max_ng, yo[2]);
-        }
-        sink.zbuf[idx] = yo[1];
-        sink.ngbuf[idx] = yo[2];
-        if (s.kout == SONIC_NOUT) {
-            // end of cycle (solvers.py:317-365)
-            bool stop = false;
-            if (s.cyc >= 1) {
-                const double rz = sqrt(s.ssq_z / (double)SONIC_NOUT) / (s.max_z - s.min_z);
-                const double rn = sqrt(s.ssq_ng / (double)SONIC_NOUT) / (s.max_ng - s.min_ng);
-                const bool stable = (rz < SONIC_CONV_THR) && (rn < SONIC_CONV_THR);
-                if (stable) stop = true;
-                else if (s.cyc >= SONIC_NCYC_CAP - 1) {
-                    stop = true;
-                    s.status |= SONIC_ST_NOCONV;
-                }
-            }
-            s.cyc++;
-            if (stop) {
-                s.phase = PH_DONE;
-                return false;
-            }
-            sink.zbuf[0] = yo[1];
-            sink.ngbuf[0] = yo[2];
-            sonic_cycle_begin(s, s.tstop, period, yo);
-            return false;
-        }
-        s.kout++;
-        s.tout = sonic_tout_at(s, s.kout);
-        s.nslast = s.nst;
-    }
-    return true;
-}
-
-// After a successful step (history updated, h/order chosen): driver-level bookkeeping.
-SONIC_HD void sonic_after_step(SonicLane& s, const SonicTables* T, const SonicSink& sink,
-                               double period) {
-    if (s.meth != s.mused) {
-        // method switch: force coefficient reload on the next step entry
-        s.jstart = -1;
-    }
-    if (!sonic_emit(s, sink, period)) return;
-    sonic_step_begin(s, T, false);
-}
-
-// Consider switching Adams <-> BDF after a successful step. Returns true if a switch was made
-// (history rescaled, step finished).
-SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicTables* T) {
+// Consider switching Adams <-> BDF after a successful step.  Returns true if a switch was
+// made (history rescaled, step finished).
+SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicTables* T,
+                                  SonicStepCtx* ctx) {
+    const double exsm = T->rk[s.nq + 1];
     if (s.meth == 1) {
         if (s.nq > 5) return false;
         double rh2;
         int nqm2;
         if (s.dsm > 100.0 * s.pnorm * SONIC_UROUND && s.pdest != 0.0) {
-            const double exsm = 1.0 / s.l;
-            double rh1 = 1.0 / (1.2 * pow(s.dsm, exsm) + 0.0000012);
+            double rh1 = sonic_rhsm0(s, T, ctx);
             double rh1it = 2.0 * rh1;
             const double pdh = s.pdlast * fabs(s.h);
-            if (pdh * rh1 > 0.00001) rh1it = T->sm1[s.nq - 1] / pdh;
+            if (pdh * rh1 > 0.00001) rh1it = sonic_div(T->sm1[s.nq - 1], pdh);
             rh1 = fmin(rh1, rh1it);
-            if (s.nq > SONIC_MXORDS) {
-                nqm2 = SONIC_MXORDS;
-                const int lm2 = SONIC_MXORDS + 1;
-                const double exm2 = 1.0 / lm2;
-                const double dm2 = sonic_mnorm(s.yh[lm2], s.ewt) / T->cm2[SONIC_MXORDS - 1];
-                rh2 = 1.0 / (1.2 * pow(dm2, exm2) + 0.0000012);
-            } else {
-                const double dm2 = s.dsm * (T->cm1[s.nq - 1] / T->cm2[s.nq - 1]);
-                rh2 = 1.0 / (1.2 * pow(dm2, exsm) + 0.0000012);
-                nqm2 = s.nq;
-            }
+            // nq <= 5 = MXORDS here, so the "reduce to MXORDS" branch cannot be taken
+            const double c12 = T->c12[s.nq - 1];
+            rh2 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c12, -T->lc21[s.nq - 1], exsm, &ctx->lds) +
+                            0.0000012);
+            nqm2 = s.nq;
             if (rh2 < 5.0 * rh1) return false;
         } else {
             if (s.irflag == 0) return false;
@@ -704,222 +802,130 @@ SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicTables* T) {
         s.miter = 2;
         s.pdlast = 0.0;
         s.nq = nqm2;
-        s.l = s.nq + 1;
-        sonic_rescale(s, T, rh2);
+        sonic_rescale(s, H, T, rh2);
         s.rmax = 10.0;
         return true;
     }
-    // currently BDF: consider Adams
-    const double exsm = 1.0 / s.l;
-    double rh1, dm1, exm1;
-    int nqm1;
-    if (SONIC_MXORDN < s.nq) {
-        nqm1 = SONIC_MXORDN;
-        const int lm1 = SONIC_MXORDN + 1;
-        exm1 = 1.0 / lm1;
-        dm1 = sonic_mnorm(s.yh[lm1], s.ewt) / T->cm1[SONIC_MXORDN - 1];
-        rh1 = 1.0 / (1.2 * pow(dm1, exm1) + 0.0000012);
-    } else {
-        dm1 = s.dsm * (T->cm2[s.nq - 1] / T->cm1[s.nq - 1]);
-        rh1 = 1.0 / (1.2 * pow(dm1, exsm) + 0.0000012);
-        nqm1 = s.nq;
-        exm1 = exsm;
-    }
+    // currently BDF (nq <= 5 <= MXORDN): consider Adams at the same order
+    const double c21 = T->c21[s.nq - 1];
+    double dm1 = s.dsm * c21;
+    double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->lc21[s.nq - 1], exsm, &ctx->lds) +
+                           0.0000012);
+    const int nqm1 = s.nq;
+    const double exm1 = exsm;
     double rh1it = 2.0 * rh1;
     const double pdh = s.pdnorm * fabs(s.h);
-    if (pdh * rh1 > 0.00001) rh1it = T->sm1[nqm1 - 1] / pdh;
+    if (pdh * rh1 > 0.00001) rh1it = sonic_div(T->sm1[nqm1 - 1], pdh);
     rh1 = fmin(rh1, rh1it);
-    const double rh2 = 1.0 / (1.2 * pow(s.dsm, exsm) + 0.0000012);
+    const double rh2 = sonic_rhsm0(s, T, ctx);
     if (rh1 * 5.0 < 5.0 * rh2) return false;
     const double alpha = fmax(0.001, rh1);
-    dm1 = pow(alpha, exm1) * dm1;
+    dm1 = sonic_powr(alpha, exm1) * dm1;
     if (dm1 <= 1000.0 * SONIC_UROUND * s.pnorm) return false;
     s.icount = 20;
     s.meth = 1;
     s.miter = 0;
     s.pdlast = 0.0;
     s.nq = nqm1;
-    s.l = s.nq + 1;
-    sonic_rescale(s, T, rh1);
+    sonic_rescale(s, H, T, rh1);
     s.rmax = 10.0;
     return true;
 }
 
-// The corrector converged: local error test, history update, order/step/method selection.
-SONIC_HD void sonic_converged(SonicLane& s, const SonicTables* T, const SonicSink& sink,
-                              double period) {
-    s.jcur = 0;
-    const double tq2 = SONIC_TESCO(s, T, 1);
-    s.dsm = (s.m == 0) ? s.del / tq2 : sonic_mnorm(s.acor, s.ewt) / tq2;
-    if (s.dsm > 1.0) {
-        // ---- error test failed ----
-        s.kflag--;
-        s.tn = s.told;
-        sonic_pascal(s, -1);
-        s.rmax = 2.0;
-        if (fabs(s.h) <= 0.0) {
-            sonic_fail(s, SONIC_ST_STEPFAIL);
-            return;
-        }
-        if (s.kflag <= -3) {
-            if (s.kflag == -10) {
-                sonic_fail(s, SONIC_ST_STEPFAIL);
-                return;
-            }
-            s.h *= 0.1;
-            s.y[0] = s.yh[0][0];
-            s.y[1] = s.yh[0][1];
-            s.y[2] = s.yh[0][2];
-            s.phase = PH_RESET;
-            return;
-        }
-        sonic_select(s, T, 0.0, 2);
-        sonic_predict(s);
-        return;
-    }
-    // ---- step accepted ----
-    s.kflag = 0;
-    s.nst++;
-    s.nsteps++;
-    s.hu = s.h;
-    s.nqu = s.nq;
-    s.mused = s.meth;
-    for (int j = 0; j < s.l; j++) {
-        const double e = SONIC_EL(s, T, j);
-        s.yh[j][0] += e * s.acor[0];
-        s.yh[j][1] += e * s.acor[1];
-        s.yh[j][2] += e * s.acor[2];
-    }
-    s.icount--;
-    bool switched = false;
-    if (s.icount < 0) switched = sonic_method_switch(s, T);
-    if (!switched) {
-        s.ialth--;
-        if (s.ialth == 0) {
-            double rhup = 0.0;
-            if (s.l != s.lmax) {
-                double d[3];
-                d[0] = s.acor[0] - s.yh[s.lmax - 1][0];
-                d[1] = s.acor[1] - s.yh[s.lmax - 1][1];
-                d[2] = s.acor[2] - s.yh[s.lmax - 1][2];
-                const double dup = sonic_mnorm(d, s.ewt) / SONIC_TESCO(s, T, 2);
-                const double exup = 1.0 / (s.l + 1);
-                rhup = 1.0 / (1.4 * pow(dup, exup) + 0.0000014);
-            }
-            sonic_select(s, T, rhup, 0);
-        } else if (s.ialth <= 1 && s.l != s.lmax) {
-            s.yh[s.lmax - 1][0] = s.acor[0];
-            s.yh[s.lmax - 1][1] = s.acor[1];
-            s.yh[s.lmax - 1][2] = s.acor[2];
-        }
-    }
-    sonic_after_step(s, T, sink, period);
-}
-
-// The corrector iteration failed to converge.
-SONIC_HD void sonic_corrector_failed(SonicLane& s, const SonicTables* T) {
-    if (s.miter != 0 && s.jcur != 1) {
-        // retry with a fresh Jacobian at the predicted state
-        s.ipup = s.miter;
-        s.m = 0;
-        s.rate = 0.0;
-        s.del = 0.0;
-        s.y[0] = s.yh[0][0];
-        s.y[1] = s.yh[0][1];
-        s.y[2] = s.yh[0][2];
-        s.phase = PH_CORR_FIRST;
-        return;
-    }
-    s.ncf++;
-    s.rmax = 2.0;
-    s.tn = s.told;
-    sonic_pascal(s, -1);
-    if (fabs(s.h) <= 0.0 || s.ncf == 10) {
-        sonic_fail(s, SONIC_ST_STEPFAIL);
-        return;
-    }
-    s.ipup = s.miter;
-    sonic_rescale(s, T, 0.25);
-    sonic_predict(s);
-}
-
-// Corrector update with the RHS value in savf (functional iteration or chord/Newton).
-SONIC_HD void sonic_corrector(SonicLane& s, const SonicTables* T, const SonicSink& sink,
-                              double period) {
-    const double el1 = SONIC_EL(s, T, 0);
-    if (s.miter == 0) {
-        double d[3];
-        for (int i = 0; i < 3; i++) {
-            s.savf[i] = s.h * s.savf[i] - s.yh[1][i];
-            d[i] = s.savf[i] - s.acor[i];
-        }
-        s.del = sonic_mnorm(d, s.ewt);
-        for (int i = 0; i < 3; i++) {
-            s.y[i] = s.yh[0][i] + el1 * s.savf[i];
-            s.acor[i] = s.savf[i];
-        }
-    } else {
-        double d[3];
-        for (int i = 0; i < 3; i++) d[i] = s.h * s.savf[i] - (s.yh[1][i] + s.acor[i]);
-        sonic_lusolve3(s.wm, s.ipvt, d);
-        s.del = sonic_mnorm(d, s.ewt);
-        for (int i = 0; i < 3; i++) {
-            s.acor[i] += d[i];
-            s.y[i] = s.yh[0][i] + el1 * s.acor[i];
-        }
-    }
-    // convergence test
-    bool conv = false;
-    if (s.del <= 100.0 * s.pnorm * SONIC_UROUND) {
-        conv = true;
-    } else if (!(s.m == 0 && s.meth == 1)) {
-        if (s.m != 0) {
-            double rm = 1024.0;
-            if (s.del <= 1024.0 * s.delp) rm = s.del / s.delp;
-            s.rate = fmax(s.rate, rm);
-            s.crate = fmax(0.2 * s.crate, rm);
-        }
-        const double dcon = s.del * fmin(1.0, 1.5 * s.crate) / (SONIC_TESCO(s, T, 1) * s.conit);
-        if (dcon <= 1.0) {
-            s.pdest = fmax(s.pdest, s.rate / fabs(s.h * el1));
-            if (s.pdest != 0.0) s.pdlast = s.pdest;
-            conv = true;
-        }
-    }
-    if (conv) {
-        sonic_converged(s, T, sink, period);
-        return;
-    }
-    s.m++;
-    if (s.m == 3 || (s.m >= 2 && s.del > 2.0 * s.delp)) {
-        sonic_corrector_failed(s, T);
-        return;
-    }
-    s.delp = s.del;
-    s.phase = PH_CORR_ITER;   // next RHS at (tn, y)
-}
-
-// Begin the finite-difference Jacobian: perturb component jcol of y.
-SONIC_HD void sonic_jac_perturb(SonicLane& s, double r0) {
+// Begin the finite-difference Jacobian column s.jcol: perturb that component of y.
+SONIC_HD void sonic_jac_perturb(SonicLane& s) {
     const int j = s.jcol;
-    const double yj = s.y[j];
-    const double r = fmax(1.4901161193847656e-08 * fabs(yj), r0 / s.ewt[j]);
+    const double yj = (j == 0) ? s.y[0] : (j == 1) ? s.y[1] : s.y[2];
+    const double wj = (j == 0) ? s.ewt[0] : (j == 1) ? s.ewt[1] : s.ewt[2];
+    const double r = fmax(1.4901161193847656e-08 * fabs(yj), sonic_div(s.jac_r0, wj));
     s.yj_save = yj;
-    s.y[j] = yj + r;
+    const double yp = yj + r;
+    if (j == 0) s.y[0] = yp;
+    else if (j == 1) s.y[1] = yp;
+    else s.y[2] = yp;
 }
 
-// One tick: consume the RHS value `f` evaluated at (sonic_eval_time, s.y) and advance the
-// lane to its next evaluation point.
-SONIC_HD void sonic_tick(SonicLane& s, const SonicTables* T, const SonicSink& sink,
-                         double period, const double f[3]) {
+// One tick: consume the RHS value `f` evaluated at (s.tn, s.y) and advance the lane to its
+// next evaluation point.  The body is a sequence of stages guarded by flags, so that lanes of
+// a warp that are in different phases still share every stage they have in common.
+SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
+                         const SonicSink& sink, double period, const double f[3]) {
     s.nfe++;
-    switch (s.phase) {
-    case PH_INIT: {
+    bool do_corr = false;      // run the corrector update with savf
+    bool do_predict = false;   // start (or redo) a step: Pascal prediction
+    int begin_mode = 0;        // 1 = first step of a problem, 2 = next step after a success
+    bool corr_failed = false;
+
+    // ---- stage A: consume the RHS value according to the phase --------------------------
+    if (s.phase == PH_CORR_FIRST || s.phase == PH_CORR_ITER) {
+        s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
+        if (s.phase == PH_CORR_FIRST && s.ipup > 0) {
+            // P = I - h el0 J must be re-evaluated: finite-difference Jacobian, 3 more ticks
+            s.nje++;
+            s.ierpj = 0;
+            s.jcur = 1;
+            const double fac = sonic_mnorm(s.savf, s.ewt);
+            double r0 = 1000.0 * fabs(s.h) * SONIC_UROUND * 3.0 * fac;
+            if (r0 == 0.0) r0 = 1.0;
+            s.jac_r0 = r0;
+            s.jcol = 0;
+            sonic_jac_perturb(s);
+            s.phase = PH_JAC;
+        } else {
+            if (s.phase == PH_CORR_FIRST) s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
+            do_corr = true;
+        }
+    } else if (s.phase == PH_JAC) {
+        const int j = s.jcol;
+        const double wj = (j == 0) ? s.ewt[0] : (j == 1) ? s.ewt[1] : s.ewt[2];
+        const double rr = fmax(1.4901161193847656e-08 * fabs(s.yj_save), sonic_div(s.jac_r0, wj));
+        const double hl0 = s.h * s.el0;
+        const double fac = -sonic_div(hl0, rr);
+        H.wm(0 + 3 * j) = (f[0] - s.savf[0]) * fac;
+        H.wm(1 + 3 * j) = (f[1] - s.savf[1]) * fac;
+        H.wm(2 + 3 * j) = (f[2] - s.savf[2]) * fac;
+        if (j == 0) s.y[0] = s.yj_save;
+        else if (j == 1) s.y[1] = s.yj_save;
+        else s.y[2] = s.yj_save;
+        if (j < 2) {
+            s.jcol = j + 1;
+            sonic_jac_perturb(s);
+        } else {
+            // norm of the Jacobian (matrix norm consistent with the weighted max-norm)
+            double an = 0.0;
+            double rew[3];
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) rew[jj] = sonic_rcp(s.ewt[jj]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double sm = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 3; jj++)
+                    sm += SONIC_QUOT(fabs(H.wm(i + 3 * jj)), s.ewt[jj], rew[jj]);
+                an = fmax(an, sm * s.ewt[i]);
+            }
+            s.pdnorm = sonic_div(an, fabs(hl0));
+            H.wm(0) += 1.0; H.wm(4) += 1.0; H.wm(8) += 1.0;
+            const int info = sonic_lu3(H, &s.ipvt);
+            s.ipup = 0;
+            s.rc = 1.0;
+            s.nslp = s.nst;
+            s.crate = 0.7;
+            if (info != 0) {
+                // singular iteration matrix: corrector failure with a current Jacobian
+                s.ierpj = 1;
+                corr_failed = true;
+            } else {
+                s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
+                do_corr = true;
+            }
+        }
+    } else if (s.phase == PH_INIT) {
         // fresh problem (one per cycle): initial step size, history, first step
-        s.yh[0][0] = s.y[0]; s.yh[0][1] = s.y[1]; s.yh[0][2] = s.y[2];
-        s.nst = 0; s.nslast = 0; s.hu = 0.0; s.nqu = 0; s.mused = 0; s.miter = 0;
+        H.yh(0, 0) = s.y[0]; H.yh(0, 1) = s.y[1]; H.yh(0, 2) = s.y[2];
+        s.nst = 0; s.nslast = 0; s.mused = 0; s.miter = 0;
         s.meth = 1; s.jstart = 0; s.nq = 1;
-        sonic_ewset(s);
+        sonic_ewset(s, H);
         const double tdist = fabs(s.tout - s.tn);
         const double w0 = fmax(fabs(s.tn), fabs(s.tout));
         double tol = SONIC_RTOL;
@@ -930,106 +936,297 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicTables* T, const SonicSink& si
         double h0 = 1.0 / sqrt(sum);
         h0 = fmin(h0, tdist);
         s.h = h0;   // tout > t always
-        s.yh[1][0] = h0 * f[0]; s.yh[1][1] = h0 * f[1]; s.yh[1][2] = h0 * f[2];
-        sonic_step_begin(s, T, true);
-        break;
-    }
-    case PH_CORR_FIRST: {
-        s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
-        if (s.ipup > 0) {
-            // P = I - h el0 J must be re-evaluated: finite-difference Jacobian, 3 more ticks
-            s.nje++;
-            s.ierpj = 0;
-            s.jcur = 1;
-            const double fac = sonic_mnorm(s.savf, s.ewt);
-            double r0 = 1000.0 * fabs(s.h) * SONIC_UROUND * 3.0 * fac;
-            if (r0 == 0.0) r0 = 1.0;
-            s.jac_r0 = r0;
-            s.jcol = 0;
-            sonic_jac_perturb(s, r0);
-            s.phase = PH_JAC;
-            break;
-        }
-        s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
-        sonic_corrector(s, T, sink, period);
-        break;
-    }
-    case PH_CORR_ITER: {
-        s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
-        sonic_corrector(s, T, sink, period);
-        break;
-    }
-    case PH_JAC: {
-        const int j = s.jcol;
-        const double r0 = s.jac_r0;
-        const double rr = fmax(1.4901161193847656e-08 * fabs(s.yj_save), r0 / s.ewt[j]);
-        const double hl0 = s.h * s.el0;
-        const double fac = -hl0 / rr;
-        s.wm[0 + 3 * j] = (f[0] - s.savf[0]) * fac;
-        s.wm[1 + 3 * j] = (f[1] - s.savf[1]) * fac;
-        s.wm[2 + 3 * j] = (f[2] - s.savf[2]) * fac;
-        s.y[j] = s.yj_save;
-        if (j < 2) {
-            s.jcol = j + 1;
-            sonic_jac_perturb(s, r0);
-            break;
-        }
-        // norm of the Jacobian (weighted max-norm consistent matrix norm)
-        double an = 0.0;
-        for (int i = 0; i < 3; i++) {
-            double sm = 0.0;
-            for (int jj = 0; jj < 3; jj++) sm += fabs(s.wm[i + 3 * jj]) / s.ewt[jj];
-            an = fmax(an, sm * s.ewt[i]);
-        }
-        s.pdnorm = an / fabs(hl0);
-        s.wm[0] += 1.0; s.wm[4] += 1.0; s.wm[8] += 1.0;
-        const int info = sonic_lu3(s.wm, s.ipvt);
-        s.ipup = 0;
-        s.rc = 1.0;
-        s.nslp = s.nst;
-        s.crate = 0.7;
-        if (info != 0) {
-            s.ierpj = 1;
-            // singular iteration matrix: treated as a corrector failure with current Jacobian
-            sonic_corrector_failed(s, T);
-            break;
-        }
-        s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
-        sonic_corrector(s, T, sink, period);
-        break;
-    }
-    case PH_RESET: {
-        s.yh[1][0] = s.h * f[0]; s.yh[1][1] = s.h * f[1]; s.yh[1][2] = s.h * f[2];
+        H.yh(1, 0) = h0 * f[0]; H.yh(1, 1) = h0 * f[1]; H.yh(1, 2) = h0 * f[2];
+        begin_mode = 1;
+    } else if (s.phase == PH_RESET) {
+        H.yh(1, 0) = s.h * f[0]; H.yh(1, 1) = s.h * f[1]; H.yh(1, 2) = s.h * f[2];
         s.ipup = s.miter;
         s.ialth = 5;
         if (s.nq != 1) {
             s.nq = 1;
-            s.l = 2;
             sonic_set_order(s, T);
         }
-        sonic_predict(s);
-        break;
+        do_predict = true;
     }
-    default:
-        break;
+
+    // ---- stage B: corrector update (functional iteration or chord/Newton) ---------------
+    bool converged = false;
+    if (do_corr) {
+        const double el1 = SONIC_EL(s, T, 0);
+        const double yh00 = H.yh(0, 0), yh01 = H.yh(0, 1), yh02 = H.yh(0, 2);
+        const double yh10 = H.yh(1, 0), yh11 = H.yh(1, 1), yh12 = H.yh(1, 2);
+        if (s.miter == 0) {
+            s.savf[0] = s.h * s.savf[0] - yh10;
+            s.savf[1] = s.h * s.savf[1] - yh11;
+            s.savf[2] = s.h * s.savf[2] - yh12;
+            s.del = sonic_mnorm3(s.savf[0] - s.acor[0], s.savf[1] - s.acor[1],
+                                 s.savf[2] - s.acor[2], s.ewt);
+            s.y[0] = yh00 + el1 * s.savf[0];
+            s.y[1] = yh01 + el1 * s.savf[1];
+            s.y[2] = yh02 + el1 * s.savf[2];
+            s.acor[0] = s.savf[0]; s.acor[1] = s.savf[1]; s.acor[2] = s.savf[2];
+        } else {
+            double d[3];
+            d[0] = s.h * s.savf[0] - (yh10 + s.acor[0]);
+            d[1] = s.h * s.savf[1] - (yh11 + s.acor[1]);
+            d[2] = s.h * s.savf[2] - (yh12 + s.acor[2]);
+            sonic_lusolve3(H, s.ipvt, d);
+            s.del = sonic_mnorm(d, s.ewt);
+            s.acor[0] += d[0]; s.acor[1] += d[1]; s.acor[2] += d[2];
+            s.y[0] = yh00 + el1 * s.acor[0];
+            s.y[1] = yh01 + el1 * s.acor[1];
+            s.y[2] = yh02 + el1 * s.acor[2];
+        }
+        // convergence test
+        if (s.del <= 100.0 * s.pnorm * SONIC_UROUND) {
+            converged = true;
+        } else if (!(s.m == 0 && s.meth == 1)) {
+            if (s.m != 0) {
+                double rm = 1024.0;
+                if (s.del <= 1024.0 * s.delp) rm = sonic_div(s.del, s.delp);
+                s.rate = fmax(s.rate, rm);
+                s.crate = fmax(0.2 * s.crate, rm);
+            }
+            const double dcon = sonic_div(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit);
+            if (dcon <= 1.0) {
+                s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));
+                if (s.pdest != 0.0) s.pdlast = s.pdest;
+                converged = true;
+            }
+        }
+        if (!converged) {
+            s.m++;
+            if (s.m == 3 || (s.m >= 2 && s.del > 2.0 * s.delp)) {
+                corr_failed = true;
+            } else {
+                s.delp = s.del;
+                s.phase = PH_CORR_ITER;   // next RHS at (tn, y)
+            }
+        }
     }
+
+    // ---- stage B': the corrector iteration failed to converge ---------------------------
+    if (corr_failed) {
+        if (s.miter != 0 && s.jcur != 1) {
+            // retry with a fresh Jacobian at the predicted state
+            s.ipup = s.miter;
+            s.m = 0;
+            s.rate = 0.0;
+            s.del = 0.0;
+            s.y[0] = H.yh(0, 0);
+            s.y[1] = H.yh(0, 1);
+            s.y[2] = H.yh(0, 2);
+            s.phase = PH_CORR_FIRST;
+        } else {
+            s.ncf++;
+            s.rmax = 2.0;
+            s.tn = s.told;
+            sonic_pascal(s, H, -1.0);
+            if (fabs(s.h) <= 0.0 || s.ncf == 10) {
+                sonic_fail(s, SONIC_ST_STEPFAIL);
+            } else {
+                s.ipup = s.miter;
+                sonic_rescale(s, H, T, 0.25);
+                do_predict = true;
+            }
+        }
+    }
+
+    // ---- stage C: local error test; accept or reject the step ---------------------------
+    bool accepted = false;
+    if (converged) {
+        s.jcur = 0;
+        const double tq2 = SONIC_TESCO(s, T, 1);
+        s.dsm = sonic_div((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), tq2);
+        if (s.dsm > 1.0) {
+            // error test failed: restore the history, shrink the step (and maybe the order)
+            s.kflag--;
+            s.tn = s.told;
+            sonic_pascal(s, H, -1.0);
+            s.rmax = 2.0;
+            if (fabs(s.h) <= 0.0 || s.kflag == -10) {
+                sonic_fail(s, SONIC_ST_STEPFAIL);
+            } else if (s.kflag <= -3) {
+                // 3+ failures: restart at order 1 with a 10x smaller step
+                s.h *= 0.1;
+                s.y[0] = H.yh(0, 0);
+                s.y[1] = H.yh(0, 1);
+                s.y[2] = H.yh(0, 2);
+                s.phase = PH_RESET;
+            } else {
+                SonicStepCtx ctx;
+                ctx.rhsm0 = ctx.lds = NAN;
+                sonic_select(s, H, T, 0.0, 2, &ctx);
+                do_predict = true;
+            }
+        } else {
+            // step accepted: update the history
+            accepted = true;
+            s.kflag = 0;
+            s.nst++;
+            s.nsteps++;
+#ifdef SONIC_TRACE
+            s.hu = s.h;
+            s.nqu = s.nq;
+#endif
+            s.mused = s.meth;
+            for (int j = 0; j <= s.nq; j++) {
+                const double e = SONIC_EL(s, T, j);
+                H.yh(j, 0) += e * s.acor[0];
+                H.yh(j, 1) += e * s.acor[1];
+                H.yh(j, 2) += e * s.acor[2];
+            }
+            s.icount--;
+            SonicStepCtx ctx;
+            ctx.rhsm0 = ctx.lds = NAN;
+            bool switched = false;
+            if (s.icount < 0) switched = sonic_method_switch(s, H, T, &ctx);
+            if (!switched) {
+                const int l = s.nq + 1;
+                const int lmax = SONIC_LMAX(s);
+                s.ialth--;
+                if (s.ialth == 0) {
+                    double rhup = 0.0;
+                    if (l != lmax) {
+                        const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
+                                                        s.acor[1] - H.yh(lmax - 1, 1),
+                                                        s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
+                        const double dup = sonic_div(dup0, SONIC_TESCO(s, T, 2));
+                        const double exup = T->rk[l + 1];
+                        rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
+                    }
+                    sonic_select(s, H, T, rhup, 0, &ctx);
+                } else if (s.ialth <= 1 && l != lmax) {
+                    H.yh(lmax - 1, 0) = s.acor[0];
+                    H.yh(lmax - 1, 1) = s.acor[1];
+                    H.yh(lmax - 1, 2) = s.acor[2];
+                }
+            }
+            if (s.meth != s.mused) s.jstart = -1;   // method switch: reload coefficients next step
+        }
+    }
+
+    // ---- stage D: emit every output sample reached; end-of-cycle logic ------------------
+    if (accepted) {
+        begin_mode = 2;
+        while ((s.tn - s.tout) * s.h >= 0.0) {
+            double yo[3];
+            sonic_interp(s, H, s.tout, yo);
+            if (s.cyc >= 1) {
+                const double dz = yo[1] - s.prev_z;
+                const double dn = yo[2] - s.prev_ng;
+                H.at(SONIC_H_SSQZ) += dz * dz;
+                H.at(SONIC_H_SSQN) += dn * dn;
+                H.at(SONIC_H_MINZ) = fmin(H.at(SONIC_H_MINZ), yo[1]);
+                H.at(SONIC_H_MAXZ) = fmax(H.at(SONIC_H_MAXZ), yo[1]);
+                H.at(SONIC_H_MINN) = fmin(H.at(SONIC_H_MINN), yo[2]);
+                H.at(SONIC_H_MAXN) = fmax(H.at(SONIC_H_MAXN), yo[2]);
+            }
+            sink.zbuf[s.kout] = yo[1];
+            sink.ngbuf[s.kout] = yo[2];
+            if (s.kout == SONIC_NOUT) {
+                // end of cycle (solvers.py:317-365)
+                bool stop = false;
+                if (s.cyc >= 1) {
+                    const double rz = sqrt(H.at(SONIC_H_SSQZ) / (double)SONIC_NOUT) /
+                                      (H.at(SONIC_H_MAXZ) - H.at(SONIC_H_MINZ));
+                    const double rn = sqrt(H.at(SONIC_H_SSQN) / (double)SONIC_NOUT) /
+                                      (H.at(SONIC_H_MAXN) - H.at(SONIC_H_MINN));
+                    const bool stable = (rz < SONIC_CONV_THR) && (rn < SONIC_CONV_THR);
+                    if (stable) stop = true;
+                    else if (s.cyc >= SONIC_NCYC_CAP - 1) {
+                        stop = true;
+                        s.status |= SONIC_ST_NOCONV;
+                    }
+                }
+                s.cyc++;
+                begin_mode = 0;
+                if (stop) {
+                    s.phase = PH_DONE;
+                } else {
+                    sink.zbuf[0] = yo[1];
+                    sink.ngbuf[0] = yo[2];
+                    sonic_cycle_begin(s, H, sink, s.tstop, period, yo);
+                }
+                break;
+            }
+            s.kout++;
+            s.tout = sonic_tout_at(s, s.kout);
+            s.nslast = s.nst;
+            if (s.cyc >= 1) {
+                s.prev_z = sink.zbuf[s.kout];
+                s.prev_ng = sink.ngbuf[s.kout];
+            }
+        }
+    }
+
+    // ---- stage E: preliminaries of the next step, then prediction ------------------------
+    if (begin_mode != 0) {
+        bool ok = true;
+        if (begin_mode == 2) {
+            if (s.nst - s.nslast >= SONIC_MXSTEP) {
+                sonic_fail(s, SONIC_ST_MXSTEP);
+                ok = false;
+            } else {
+                sonic_ewset(s, H);
+            }
+        }
+        // (the "too much accuracy requested" test of the original driver cannot fire here:
+        //  |y| * ewt <= 1 / rtol = 6.7e7, far below 1 / uround)
+        if (ok) {
+            s.kflag = 0;
+            s.told = s.tn;
+            s.ncf = 0;
+            s.ierpj = 0;
+            s.jcur = 0;
+            s.delp = 0.0;
+            if (s.jstart == 0) {
+                s.nq = 1;
+                s.ialth = 2;
+                s.rmax = 10000.0;
+                s.rc = 0.0;
+                s.el0 = 1.0;
+                s.crate = 0.7;
+                s.nslp = 0;
+                s.ipup = s.miter;
+                s.icount = 20;
+                s.irflag = 0;
+                s.pdest = 0.0;
+                s.pdlast = 0.0;
+                s.tab_meth = 1;
+                sonic_set_order(s, T);
+            } else if (s.jstart == -1) {
+                s.ipup = s.miter;
+                if (s.ialth == 1) s.ialth = 2;
+                if (s.meth != s.mused) {
+                    s.tab_meth = s.meth;
+                    s.ialth = s.nq + 1;
+                    sonic_set_order(s, T);
+                }
+            }
+            s.jstart = 1;
+            do_predict = true;
+        }
+    }
+    if (do_predict) sonic_predict(s, H);
 }
 
 // Start a lane on its grid point with a precomputed initial deflection.
 // y0 = (0, Z0, ng0) (bls.py:737-747).
-SONIC_HD void sonic_lane_start(SonicLane& s, const SonicPoint& p, double f, double z0,
-                               const SonicSink& sink) {
+SONIC_HD void sonic_lane_start(SonicLane& s, const SonicHist& H, const SonicPoint& p, double f,
+                               double z0, const SonicSink& sink) {
     s.status = SONIC_ST_OK;
     s.nfe = s.nje = s.nsteps = 0;
     s.cyc = 0;
     const double y0[3] = {0.0, z0, p.ng0};
     sink.zbuf[0] = z0;
     sink.ngbuf[0] = p.ng0;
-    sonic_cycle_begin(s, 0.0, 1.0 / f, y0);
+    sonic_cycle_begin(s, H, sink, 0.0, 1.0 / f, y0);
 }
 
 // Same, computing the initial deflection in place.
-SONIC_HD void sonic_lane_init(SonicLane& s, const SonicPoint& p, double f, const SonicSink& sink) {
+SONIC_HD void sonic_lane_init(SonicLane& s, const SonicHist& H, const SonicPoint& p, double f,
+                              const SonicSink& sink) {
     double z0;
     if (!sonic_z0(p, f, &z0)) {
         s.status = SONIC_ST_Z0FAIL;
@@ -1038,7 +1235,7 @@ SONIC_HD void sonic_lane_init(SonicLane& s, const SonicPoint& p, double f, const
         s.phase = PH_DONE;
         return;
     }
-    sonic_lane_start(s, p, f, z0, sink);
+    sonic_lane_start(s, H, p, f, z0, sink);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1123,5 +1320,12 @@ static void sonic_fill_tables(SonicTables* T) {
     static const double sm1[12] = {0.5, 0.575, 0.55, 0.45, 0.35, 0.25, 0.2, 0.15, 0.1, 0.075, 0.05,
                                    0.025};
     for (int i = 0; i < 12; i++) T->sm1[i] = sm1[i];
+    for (int i = 0; i < 5; i++) T->lc21[i] = log(T->cm2[i] / T->cm1[i]);
+    for (int i = 0; i < 5; i++) {
+        T->c21[i] = T->cm2[i] / T->cm1[i];
+        T->c12[i] = T->cm1[i] / T->cm2[i];
+    }
+    T->rk[0] = 0.0;
+    for (int i = 1; i < 16; i++) T->rk[i] = 1.0 / i;
 }
 

@@ -9,6 +9,7 @@
         python tests/golden/make_goldens.py c1          # BASELINE config 1 (1000 points)
         python tests/golden/make_goldens.py neurons     # small grids for the C3-C5 neurons
         python tests/golden/make_goldens.py c2sub       # stratified subsample of RS-4D (C2)
+        python tests/golden/make_goldens.py noise       # reference re-run with +-2 ulp amplitude
         python tests/golden/make_goldens.py all
 
     Every record is produced by `NeuronalBilayerSonophore.computeEffVars`
@@ -180,8 +181,12 @@ def gen_rates():
     print('rates_sweep.json:', len(names), 'neurons x', Vm.size, 'potentials')
 
 
-def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref):
-    jobs = [(name, a, f, A, Q, list(fsref)) for a in aref for f in fref for A in Aref for Q in Qref]
+def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref, amp_scale=1.0):
+    # amp_scale != 1 (a 1-2 ulp relative change of the drive amplitude) is used to measure the
+    # reference's own reproducibility floor: how far its outputs move under a rounding-level
+    # perturbation of its inputs.
+    jobs = [(name, a, f, A * amp_scale, Q, list(fsref))
+            for a in aref for f in fref for A in Aref for Q in Qref]
     t0 = time.perf_counter()
     recs = pmap(jobs)
     wall = time.perf_counter() - t0
@@ -198,11 +203,11 @@ def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref):
     print(f'{fname}: {len(jobs)} points in {wall:.1f} s on {mp.cpu_count()} processes')
 
 
-def gen_c1():
+def gen_c1(amp_scale=1.0, tag=''):
     ''' BASELINE config 1 (SURVEY 8d "C1"). '''
     A = np.insert(np.logspace(np.log10(0.1), np.log10(600), 19), 0, 0.) * 1e3
     Q = np.linspace(-107e-5, 50e-5, 50)
-    _grid_to_npz('c1_RS_32nm_500kHz.npz', 'RS', [32e-9], [500e3], A, Q, [1.0])
+    _grid_to_npz(f'c1_RS_32nm_500kHz{tag}.npz', 'RS', [32e-9], [500e3], A, Q, [1.0], amp_scale)
 
 
 def gen_neurons():
@@ -224,19 +229,29 @@ def gen_neurons():
                  Q[::24], np.arange(1, 101)[::11] * 1e-2)
 
 
-def gen_c2sub():
+def gen_c2sub(amp_scale=1.0, tag=''):
     ''' Stratified subsample of the RS 4-D default grid (SURVEY 8d "C2"). '''
-    A = c2_amps()[::7]            # 8 amplitudes incl. 0 and ~386 kPa
+    A = c2_amps()[::7]            # 8 amplitudes incl. 0 and ~502 kPa
     A = np.append(A, c2_amps()[-1])
     Q = default_charges('RS')[::22]
-    _grid_to_npz('c2_RS_sub.npz', 'RS', [16e-9, 32e-9, 64e-9],
-                 [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0])
+    _grid_to_npz(f'c2_RS_sub{tag}.npz', 'RS', [16e-9, 32e-9, 64e-9],
+                 [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
+
+
+def gen_noise():
+    ''' The reference re-run with the drive amplitude changed by +-2 ulp: its own
+        reproducibility floor on the C1 grid and the C2 subsample. '''
+    up, dn = 1.0 + 4.440892098500626e-16, 1.0 - 4.440892098500626e-16
+    gen_c1(up, '_ulp_up')
+    gen_c1(dn, '_ulp_dn')
+    gen_c2sub(up, '_ulp_up')
+    gen_c2sub(dn, '_ulp_dn')
 
 
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
-            'c2sub': gen_c2sub}
+            'c2sub': gen_c2sub, 'noise': gen_noise}
     for k, fn in todo.items():
         if what in (k, 'all'):
             fn()

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define SONIC_TRACE 1
 #include "../../pysonic_b200/csrc/sonic_core.h"
 
 static SonicTables g_tab;
@@ -41,10 +42,14 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     SonicPoint p;
     sonic_point_init(p, b, f, A, Q);
     SonicSink sink;
-    sink.zbuf = zbuf; sink.ngbuf = ngbuf; sink.stride = 1;
+    sink.zbuf = zbuf; sink.ngbuf = ngbuf;
     SonicLane s;
     memset(&s, 0, sizeof(s));
-    sonic_lane_init(s, p, f, sink);
+    double hist[SONIC_H_SIZE];
+    memset(hist, 0, sizeof(hist));
+    SonicHist H;
+    H.base = hist;
+    sonic_lane_init(s, H, p, f, sink);
     const double period = 1.0 / f;
     long nticks = 0, nrows = 0;
     unsigned last_nsteps = 0;
@@ -52,9 +57,8 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     unsigned nfe_base = 0, nje_base = 0;
     while (s.phase != PH_DONE) {
         double fv[3];
-        if (sonic_rhs(p, sonic_eval_time(s), s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-        // snapshot of integrator statistics as they will stand when this tick emits
-        sonic_tick(s, &g_tab, sink, period, fv);
+        if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
+        sonic_tick(s, H, &g_tab, sink, period, fv);
         nticks++;
         if (g_steplog && s.nsteps != last_nsteps && g_steplog_n < g_steplog_max) {
             double* r = g_steplog + 8 * g_steplog_n++;
