@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
         }
         const bool active = pt >= 0;
         if (!__any_sync(0xffffffffu, active || can_work)) break;
+        const unsigned wmask = __ballot_sync(0xffffffffu, active);
         if (active) {
             double fv[3];
             if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-            sonic_tick(s, H, &tab, sink, period, fv);
+            sonic_tick(s, H, &tab, sink, period, fv, wmask);
             if (s.phase == PH_DONE) {
                 job.ncycles[pt] = s.cyc;
                 job.status[pt] = s.status;

@@ -41,6 +41,14 @@
 #else
 #define SONIC_DIVC(x, c) ((x) * (1.0 / (c)))
 #endif
+// Stage boundary of the tick: re-converge the lanes of the warp that entered the tick (they
+// took different branches inside the previous stage) so that the next stage is executed once,
+// by all lanes that need it, instead of once per divergent path.
+#if defined(__CUDA_ARCH__)
+#define SONIC_STAGE_SYNC(mask) __syncwarp(mask)
+#else
+#define SONIC_STAGE_SYNC(mask) ((void)0)
+#endif
 // x / y where a reciprocal r of y is already at hand: the host build divides exactly.
 #if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
 #define SONIC_QUOT(x, y, r) ((x) * (r))
@@ -849,7 +857,9 @@ SONIC_HD void sonic_jac_perturb(SonicLane& s) {
 // next evaluation point.  The body is a sequence of stages guarded by flags, so that lanes of
 // a warp that are in different phases still share every stage they have in common.
 SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
-                         const SonicSink& sink, double period, const double f[3]) {
+                         const SonicSink& sink, double period, const double f[3],
+                         unsigned wmask) {
+    (void)wmask;
     s.nfe++;
     bool do_corr = false;      // run the corrector update with savf
     bool do_predict = false;   // start (or redo) a step: Pascal prediction
@@ -949,6 +959,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         do_predict = true;
     }
 
+    SONIC_STAGE_SYNC(wmask);
     // ---- stage B: corrector update (functional iteration or chord/Newton) ---------------
     bool converged = false;
     if (do_corr) {
@@ -1005,7 +1016,17 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         }
     }
 
-    // ---- stage B': the corrector iteration failed to converge ---------------------------
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage R: retraction after a failed corrector iteration or a failed error test ---
+    // (both restore tn and the history before shrinking the step)
+    bool err_failed = false;
+    if (converged) {
+        s.jcur = 0;
+        const double tq2 = SONIC_TESCO(s, T, 1);
+        s.dsm = sonic_div((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), tq2);
+        err_failed = s.dsm > 1.0;
+    }
+    bool cf_retract = false;
     if (corr_failed) {
         if (s.miter != 0 && s.jcur != 1) {
             // retry with a fresh Jacobian at the predicted state
@@ -1018,10 +1039,19 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
             s.y[2] = H.yh(0, 2);
             s.phase = PH_CORR_FIRST;
         } else {
+            cf_retract = true;
+        }
+    }
+    int sel_mode = 0;          // 1 = order/step selection after a success, 2 = after a failure
+    double sel_rhup = 0.0;
+    SonicStepCtx ctx;
+    ctx.rhsm0 = ctx.lds = NAN;
+    if (cf_retract || err_failed) {
+        s.tn = s.told;
+        sonic_pascal(s, H, -1.0);
+        s.rmax = 2.0;
+        if (cf_retract) {
             s.ncf++;
-            s.rmax = 2.0;
-            s.tn = s.told;
-            sonic_pascal(s, H, -1.0);
             if (fabs(s.h) <= 0.0 || s.ncf == 10) {
                 sonic_fail(s, SONIC_ST_STEPFAIL);
             } else {
@@ -1029,21 +1059,9 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                 sonic_rescale(s, H, T, 0.25);
                 do_predict = true;
             }
-        }
-    }
-
-    // ---- stage C: local error test; accept or reject the step ---------------------------
-    bool accepted = false;
-    if (converged) {
-        s.jcur = 0;
-        const double tq2 = SONIC_TESCO(s, T, 1);
-        s.dsm = sonic_div((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), tq2);
-        if (s.dsm > 1.0) {
-            // error test failed: restore the history, shrink the step (and maybe the order)
+        } else {
+            // error test failed: shrink the step (and maybe the order)
             s.kflag--;
-            s.tn = s.told;
-            sonic_pascal(s, H, -1.0);
-            s.rmax = 2.0;
             if (fabs(s.h) <= 0.0 || s.kflag == -10) {
                 sonic_fail(s, SONIC_ST_STEPFAIL);
             } else if (s.kflag <= -3) {
@@ -1054,58 +1072,72 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                 s.y[2] = H.yh(0, 2);
                 s.phase = PH_RESET;
             } else {
-                SonicStepCtx ctx;
-                ctx.rhsm0 = ctx.lds = NAN;
-                sonic_select(s, H, T, 0.0, 2, &ctx);
-                do_predict = true;
+                sel_mode = 2;
             }
-        } else {
-            // step accepted: update the history
-            accepted = true;
-            s.kflag = 0;
-            s.nst++;
-            s.nsteps++;
-#ifdef SONIC_TRACE
-            s.hu = s.h;
-            s.nqu = s.nq;
-#endif
-            s.mused = s.meth;
-            for (int j = 0; j <= s.nq; j++) {
-                const double e = SONIC_EL(s, T, j);
-                H.yh(j, 0) += e * s.acor[0];
-                H.yh(j, 1) += e * s.acor[1];
-                H.yh(j, 2) += e * s.acor[2];
-            }
-            s.icount--;
-            SonicStepCtx ctx;
-            ctx.rhsm0 = ctx.lds = NAN;
-            bool switched = false;
-            if (s.icount < 0) switched = sonic_method_switch(s, H, T, &ctx);
-            if (!switched) {
-                const int l = s.nq + 1;
-                const int lmax = SONIC_LMAX(s);
-                s.ialth--;
-                if (s.ialth == 0) {
-                    double rhup = 0.0;
-                    if (l != lmax) {
-                        const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
-                                                        s.acor[1] - H.yh(lmax - 1, 1),
-                                                        s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
-                        const double dup = sonic_div(dup0, SONIC_TESCO(s, T, 2));
-                        const double exup = T->rk[l + 1];
-                        rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
-                    }
-                    sonic_select(s, H, T, rhup, 0, &ctx);
-                } else if (s.ialth <= 1 && l != lmax) {
-                    H.yh(lmax - 1, 0) = s.acor[0];
-                    H.yh(lmax - 1, 1) = s.acor[1];
-                    H.yh(lmax - 1, 2) = s.acor[2];
-                }
-            }
-            if (s.meth != s.mused) s.jstart = -1;   // method switch: reload coefficients next step
         }
     }
 
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage C: the step is accepted: update the history -------------------------------
+    const bool accepted = converged && !err_failed;
+    bool do_mswitch = false;
+    if (accepted) {
+        s.kflag = 0;
+        s.nst++;
+        s.nsteps++;
+#ifdef SONIC_TRACE
+        s.hu = s.h;
+        s.nqu = s.nq;
+#endif
+        s.mused = s.meth;
+        for (int j = 0; j <= s.nq; j++) {
+            const double e = SONIC_EL(s, T, j);
+            H.yh(j, 0) += e * s.acor[0];
+            H.yh(j, 1) += e * s.acor[1];
+            H.yh(j, 2) += e * s.acor[2];
+        }
+        s.icount--;
+        do_mswitch = s.icount < 0;
+    }
+
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage C2: consider switching between the Adams and BDF families -----------------
+    bool switched = false;
+    if (do_mswitch) switched = sonic_method_switch(s, H, T, &ctx);
+
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage C3: step/order bookkeeping after a success ---------------------------------
+    if (accepted && !switched) {
+        const int l = s.nq + 1;
+        const int lmax = SONIC_LMAX(s);
+        s.ialth--;
+        if (s.ialth == 0) {
+            if (l != lmax) {
+                const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
+                                                s.acor[1] - H.yh(lmax - 1, 1),
+                                                s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
+                const double dup = sonic_div(dup0, SONIC_TESCO(s, T, 2));
+                const double exup = T->rk[l + 1];
+                sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
+            }
+            sel_mode = 1;
+        } else if (s.ialth <= 1 && l != lmax) {
+            H.yh(lmax - 1, 0) = s.acor[0];
+            H.yh(lmax - 1, 1) = s.acor[1];
+            H.yh(lmax - 1, 2) = s.acor[2];
+        }
+    }
+
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage C4: order and step-size selection (after a success or a failed error test) -
+    if (sel_mode != 0) {
+        const bool redo = sonic_select(s, H, T, sel_rhup, sel_mode == 2 ? 2 : 0, &ctx);
+        if (sel_mode == 2) do_predict = true;
+        (void)redo;
+    }
+    if (accepted && s.meth != s.mused) s.jstart = -1;   // method switch: reload coefficients
+
+    SONIC_STAGE_SYNC(wmask);
     // ---- stage D: emit every output sample reached; end-of-cycle logic ------------------
     if (accepted) {
         begin_mode = 2;
@@ -1160,7 +1192,8 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         }
     }
 
-    // ---- stage E: preliminaries of the next step, then prediction ------------------------
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage E: preliminaries of the next step ------------------------------------------
     if (begin_mode != 0) {
         bool ok = true;
         if (begin_mode == 2) {
@@ -1208,6 +1241,9 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
             do_predict = true;
         }
     }
+
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage F: prediction (start or redo a step) ---------------------------------------
     if (do_predict) sonic_predict(s, H);
 }
 

@@ -65,6 +65,7 @@ def main():
     data = rows[2:]
     iE = hdr.index('Instructions Executed')
     iS = hdr.index('# Samples')
+    iT = hdr.index('Thread Instructions Executed')
     sass = sass_lines(so, kernel)
     if len(sass) != len(data):
         print(f'WARNING: instruction count mismatch: nvdisasm {len(sass)} vs ncu {len(data)} '
@@ -73,7 +74,7 @@ def main():
     here = os.path.dirname(os.path.abspath(__file__))
     fmaps = {'sonic_core.h': function_map(os.path.join(here, '..', 'pysonic_b200', 'csrc', 'sonic_core.h')),
              'sonic_b200.cu': function_map(os.path.join(here, '..', 'pysonic_b200', 'csrc', 'sonic_b200.cu'))}
-    per_line, per_fn, samples_fn = {}, {}, {}
+    per_line, per_fn, samples_fn, thr_fn = {}, {}, {}, {}
     total = 0
     for k in range(n):
         e = int(data[k][iE])
@@ -84,11 +85,12 @@ def main():
         fn = fmaps.get(fname, {}).get(line, fname)
         per_fn[fn] = per_fn.get(fn, 0) + e
         samples_fn[fn] = samples_fn.get(fn, 0) + sm
+        thr_fn[fn] = thr_fn.get(fn, 0) + int(data[k][iT])
     tot_s = sum(samples_fn.values()) or 1
     print(f'total executed warp-instructions: {total}  ({total / nticks:.1f} per tick)')
     print('--- per function (instructions per tick, share, stall-sample share)')
     for fn, e in sorted(per_fn.items(), key=lambda x: -x[1])[:40]:
-        print(f'{fn:34s} {e / nticks:9.1f} {100 * e / total:6.1f}%  samples {100 * samples_fn[fn] / tot_s:5.1f}%')
+        print(f'{fn:34s} {e / nticks:9.1f} {100 * e / total:6.1f}%  samples {100 * samples_fn[fn] / tot_s:5.1f}%  threads/inst {thr_fn[fn] / max(e, 1):5.1f}')
     print('--- top source lines')
     for (fname, line), e in sorted(per_line.items(), key=lambda x: -x[1])[:40]:
         print(f'{fname}:{line:<5d} {e / nticks:9.1f} {100 * e / total:6.1f}%')
