@@ -138,6 +138,18 @@ def gen_points():
         ('IB', 32e-9, 500e3, 100e3, -71.4e-5, [1.0]),
     ]
     recs = pmap(jobs)
+    # the reference's own reproducibility on each point: re-run with A * (1 +- 2 ulp)
+    for scale in (1.0 + 4.440892098500626e-16, 1.0 - 4.440892098500626e-16):
+        pert = pmap([(j[0], j[1], j[2], j[3] * scale, j[4], j[5]) for j in jobs])
+        for r, q in zip(recs, pert):
+            dev = 0.0
+            for ev, evq in zip(r['effvars'], q['effvars']):
+                for k in ev:
+                    d = abs(ev[k] - evq[k])
+                    if d >= 1e-9:
+                        dev = max(dev, d / abs(ev[k]))
+            r['self_noise'] = max(r.get('self_noise', 0.0), dev)
+            r.setdefault('ncycles_ulp', []).append(q['ncycles'])
     # constants of the sonophore instances, for the host-side parameter tests
     consts = {}
     for name, a in sorted({(j[0], j[1]) for j in jobs}):

@@ -1,0 +1,160 @@
+# -*- coding: utf-8 -*-
+''' Host-side mirror of the reference interfaces on the lookup path: descriptors, grid
+    validation, queue order, file naming, pickle format.  No GPU needed. '''
+
+import logging
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import pysonic_b200 as ps
+from pysonic_b200 import codegen
+from pysonic_b200.batches import Batch
+from pysonic_b200.neurons import NEURON_ORDER, NEURON_SPECS, spec_rate_names
+from pysonic_b200.parallel import predicted_log_cost, shard_indices
+from pysonic_b200.run_lookups import _parser, _validate
+
+
+def test_neuron_descriptors_match_reference(points_golden):
+    for key, c in points_golden['consts'].items():
+        name, a = key.split('@')
+        a = float(a[:-2]) * 1e-9
+        pn = ps.getPointNeuron(name)
+        assert pn.rates == c['rates']
+        assert pn.Cm0 == c['Cm0'] and pn.Qm0 == c['Qm0']
+        np.testing.assert_array_equal(pn.Qbounds, c['Qbounds'])
+        nbls = ps.NeuronalBilayerSonophore(a, pn)
+        assert nbls.Delta == c['Delta'] and nbls.ng0 == c['ng0'] and nbls.V0 == c['V0']
+        assert nbls.Zmin == c['Zmin'] and nbls.S0 == c['S0']
+        assert nbls.LJ_approx == c['LJ']
+        p = nbls.abi_params()
+        assert set(p) == {'a', 'Delta', 'x0', 'C', 'nrep', 'nattr', 'Cm0', 'depth'}
+
+
+def test_rates_golden_neurons_all_declared(rates_golden):
+    assert set(rates_golden['neurons']) == set(NEURON_ORDER)
+    for name, rec in rates_golden['neurons'].items():
+        assert spec_rate_names(name) == rec['rates']
+        assert NEURON_SPECS[name]['Cm0'] == rec['Cm0'] and NEURON_SPECS[name]['Vm0'] == rec['Vm0']
+
+
+def test_unknown_neuron_and_radius():
+    with pytest.raises(ValueError):
+        ps.getPointNeuron('XYZ')
+    with pytest.raises(ValueError, match='no precomputed'):
+        ps.NeuronalBilayerSonophore(33.3e-9, ps.getPointNeuron('RS'))
+    with pytest.raises(ValueError):
+        ps.BilayerSonophore(-1e-9, 1e-2, -7e-4)
+
+
+def test_acoustic_drive_checks():
+    d = ps.AcousticDrive(500e3, 100e3)
+    assert d.dt == 1 / (1000 * 500e3) and d.periodicity == 1 / 500e3 and d.nPerCycle == 1000
+    assert d.compute(0.) == pytest.approx(100e3 * np.sin(-np.pi))
+    with pytest.raises(ValueError):
+        ps.AcousticDrive(0., 1e3)
+    with pytest.raises(ValueError):
+        ps.AcousticDrive(1e3, -1.)
+    with pytest.raises(TypeError):
+        ps.AcousticDrive('500', 1e3)
+    q = ps.AcousticDrive.createQueue([1e5, 2e5], [0., 1e3, 2e3])
+    assert [(x.f, x.A) for x in q] == [(1e5, 0.), (1e5, 1e3), (1e5, 2e3), (2e5, 0.), (2e5, 1e3), (2e5, 2e3)]
+
+
+def test_grid_validation_mirrors_reference():
+    ''' run_lookups.py:85-96 and :58-60: same exception types. '''
+    pn = ps.getPointNeuron('RS')
+    a, f, A, fs, Q = (np.array([32e-9]), np.array([500e3]), np.array([0., 1e5]), np.array([1.]),
+                      np.array([-7e-4, 0.]))
+    with pytest.raises(TypeError):
+        ps.computeAStimLookup(pn, a, f, np.array([0, 100000]), fs, Q)        # int typed
+    with pytest.raises(TypeError):
+        ps.computeAStimLookup(pn, 32e-9, f, A, fs, Q)                        # not iterable
+    with pytest.raises(ValueError):
+        ps.computeAStimLookup(pn, a, np.array([]), A, fs, Q)                 # empty
+    with pytest.raises(ValueError):
+        ps.computeAStimLookup(pn, np.array([-1e-9]), f, A, fs, Q)            # non-positive radius
+    with pytest.raises(ValueError):
+        ps.computeAStimLookup(pn, a, f, np.array([-1.]), fs, Q)              # negative amplitude
+    with pytest.raises(AssertionError):
+        ps.computeAStimLookup(pn, a, np.array([1e5, 5e5]), A, np.array([0.5, 1.]), Q)   # fs sweep, 2 f
+    with pytest.raises(NotImplementedError):
+        ps.computeAStimLookup(pn, a, f, A, fs, Q, novertones=1)
+    _validate({'a': list(a), 'f': list(f), 'A': list(A), 'Q': list(Q), 'fs': list(fs)})
+
+
+def test_lookup_file_names():
+    nbls = ps.NeuronalBilayerSonophore(32e-9, ps.getPointNeuron('RS'))
+    assert nbls.getLookupFileName() == 'RS_lookups_fs1.00.pkl'
+    assert nbls.getLookupFileName(a=32e-9, f=500e3, fs=1.) == 'RS_lookups_32nm_500kHz_fs1.00.pkl'
+    assert nbls.getLookupFileName(a=32e-9, f=500e3, A=1e5) == 'RS_lookups_32nm_500kHz_100kPa.pkl'
+    assert nbls.getLookupFileName(fs=0.75, novertones=2) == 'RS_lookups_fs0.75_2overtones.pkl'
+
+
+def test_lookup_pickle_format(tmp_path):
+    ''' {'refs': dict(a, f, A, Q, fs), 'tables': dict(V, rates..., tcomp)} of plain ndarrays
+        (lookups.py:381-392); readable without this package. '''
+    refs = {'a': np.array([32e-9]), 'f': np.array([5e5]), 'A': np.array([0., 1e5]),
+            'Q': np.array([-1e-3, 0., 1e-3]), 'fs': np.array([1.])}
+    dims = (1, 1, 2, 3, 1)
+    tables = {k: np.random.default_rng(0).random(dims) for k in ['V', 'alpham', 'betam', 'tcomp']}
+    lkp = ps.Lookup(refs, tables)
+    assert repr(lkp) == 'Lookup5D(a: 1, f: 1, A: 2, Q: 3, fs: 1)[V, alpham, betam, tcomp]'
+    fpath = os.path.join(tmp_path, 'x.pkl')
+    lkp.toPickle(fpath)
+    with open(fpath, 'rb') as fh:
+        d = pickle.load(fh)
+    assert list(d.keys()) == ['refs', 'tables']
+    assert type(d['refs']) is dict and type(d['tables']) is dict
+    assert list(d['refs'].keys()) == ['a', 'f', 'A', 'Q', 'fs']
+    assert list(d['tables'].keys()) == ['V', 'alpham', 'betam', 'tcomp']
+    for v in d['tables'].values():
+        assert type(v) is np.ndarray and v.dtype == np.float64 and v.shape == dims
+    back = ps.Lookup.fromPickle(fpath)
+    np.testing.assert_array_equal(back['V'], tables['V'])
+    with pytest.raises(ValueError):
+        ps.Lookup(refs, {'V': np.zeros((1, 1, 2, 3))})
+    with pytest.raises(FileNotFoundError):
+        ps.Lookup.fromPickle(os.path.join(tmp_path, 'missing.pkl'))
+
+
+def test_batch_generic_function_and_queue_order():
+    out = Batch(lambda x, y=0: x + y, [[1], ([2], {'y': 5}), [3]])(mpi=False, loglevel=logging.ERROR)
+    assert out == [1, 7, 3]
+    q = Batch.createQueue([1., 2.], [10., 20., 30.])
+    assert q == [[1., 10.], [1., 20.], [1., 30.], [2., 10.], [2., 20.], [2., 30.]]
+    q3 = Batch.createQueue([1., 2.], [10., 20.], [5., 6.])
+    assert q3[0] == [1., 10., 5.] and q3[1] == [1., 10., 6.] and q3[-1] == [2., 20., 6.]
+
+
+def test_cli_defaults_match_reference():
+    ''' run_lookups.py:183-188 and parsers.py:439-448 '''
+    args = _parser().parse_args([])
+    assert args.neuron == ['RS'] and args.radius == [16.0, 32.0, 64.0]
+    assert args.freq == [20., 100., 500., 1e3, 2e3, 3e3, 4e3]
+    assert args.fs == [100.] and not args.spanFs and not args.mpi and not args.test
+    args = _parser().parse_args('-n STN -a 32 -f 500 --spanFs --mpi --test'.split())
+    assert args.neuron == ['STN'] and args.spanFs and args.mpi and args.test
+
+
+def test_codegen_is_committed_and_deterministic():
+    path = os.path.join(os.path.dirname(codegen.__file__), 'csrc', 'generated', 'neuron_rates.cuh')
+    with open(path) as fh:
+        assert fh.read() == codegen.generate()
+    text = codegen.generate()
+    for i, n in enumerate(NEURON_ORDER):
+        assert f'template <> struct SonicRates<{i}>' in text and f'// ---- {n} ----' in text
+
+
+def test_cost_sharding_round_robin():
+    a = np.full(8, 32e-9)
+    f = np.array([2e4, 5e5, 4e6, 2e4, 5e5, 4e6, 1e5, 1e6])
+    A = np.array([6e5, 6e5, 6e5, 0., 1e3, 1e4, 3e5, 1e5])
+    cost = predicted_log_cost(a, f, A)
+    assert np.argmax(cost) == 0           # 20 kHz / 600 kPa is the dearest point
+    parts = [shard_indices(cost, r, 3) for r in range(3)]
+    assert sorted(np.concatenate(parts).tolist()) == list(range(8))
+    order = np.argsort(-cost, kind='stable')
+    assert [p[0] for p in parts] == order[:3].tolist()
