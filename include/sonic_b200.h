@@ -126,6 +126,10 @@ typedef struct SonicPlan SonicPlan;
 int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
                       const int32_t* ia, const double* f, const double* A, const double* Q,
                       const double* fs, int nfs, SonicPlan** plan);
+/* Launch on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of
+ * the plan's private one, so that the caller can order and time the launches with its own
+ * events.  The stream must belong to the plan's device and outlive the plan. */
+int sonic_plan_set_stream(SonicPlan* plan, void* stream);
 int sonic_plan_launch(SonicPlan* plan);   /* asynchronous on the plan's stream */
 int sonic_plan_sync(SonicPlan* plan);
 int sonic_plan_fetch(SonicPlan* plan, double* out_tables, int32_t* out_ncycles,

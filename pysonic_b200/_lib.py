@@ -55,6 +55,7 @@ EXPORTS = {
                                    C.c_int, C.c_uint32, _dp, _ip, _up, _dp, _sp]),
     'sonic_plan_create': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, _dp,
                                     C.c_int, C.POINTER(C.c_void_p)]),
+    'sonic_plan_set_stream': (C.c_int, [C.c_void_p, C.c_void_p]),
     'sonic_plan_launch': (C.c_int, [C.c_void_p]),
     'sonic_plan_sync': (C.c_int, [C.c_void_p]),
     'sonic_plan_fetch': (C.c_int, [C.c_void_p, _dp, _ip, _up, _dp, _up]),
@@ -163,6 +164,10 @@ class Plan:
         check(lib.sonic_plan_create(device, self._bls, len(bls_params), neuron_id, self.n,
                                     self.ia.ctypes.data_as(_ip), _d(self.f), _d(self.A), _d(self.Q),
                                     _d(self.fs), self.nfs, C.byref(self._h)))
+
+    def set_stream(self, cuda_stream):
+        ''' Launch on a caller-owned stream (integer cudaStream_t handle). '''
+        check(load().sonic_plan_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
     def launch(self):
         check(load().sonic_plan_launch(self._h))

@@ -319,6 +319,7 @@ struct SonicPlan {
     long long slots = 0;
     int grid = 0, lanes_per_warp = 32;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // device buffers
     SonicBls* d_radii = nullptr;
@@ -347,7 +348,7 @@ static int plan_free(SonicPlan* p) {
     cudaFree(p->d_counter);
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
     delete p;
     return SONIC_OK;
 }
@@ -578,6 +579,16 @@ int sonic_plan_launch(SonicPlan* p) {
     CUDA_TRY(cudaGetLastError());
     p->launches += 3;
     p->launched = true;
+    return SONIC_OK;
+}
+
+int sonic_plan_set_stream(SonicPlan* p, void* stream) {
+    if (!p) return set_err(SONIC_E_ARG, "null plan");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
+    p->stream = static_cast<cudaStream_t>(stream);
+    p->own_stream = false;
     return SONIC_OK;
 }
 

@@ -49,7 +49,8 @@ def _validate(refs):
 
 
 def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
-                       test=False, mpi=False, loglevel=logging.INFO, return_info=False):
+                       test=False, mpi=False, loglevel=logging.INFO, return_info=False,
+                       device=None, shard=True):
     ''' Effective-variable lookup tables over (a, f, A, Q, fs).
 
         Drop-in for `computeAStimLookup` of scripts/run_lookups.py:22: same arguments (SI units:
@@ -57,6 +58,10 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
         key order (`V`, rates in `pneuron.rates` order, `tcomp`).  `mpi=True` means "use every
         available GPU": under `torchrun` the grid is sharded over the ranks (one process per
         GPU), otherwise over the visible devices of this process.
+
+        Extra keyword arguments (not in the reference): `return_info` also returns the per-point
+        cycle counts / status words / run statistics; `device` pins the run to one CUDA device;
+        `shard=False` makes a rank under `torchrun` compute the whole grid on its own device.
 
         :return: Lookup (and, if return_info, a dict with ncycles/status/stats)
     '''
@@ -84,7 +89,7 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
     bls_params = [NeuronalBilayerSonophore(float(a), pneuron).abi_params() for a in refs['a']]
     rank, world, local_rank = dist_info()
     t0 = time.perf_counter()
-    if world > 1:
+    if world > 1 and shard:
         # one process per GPU: shard the flattened (a > f > A > Q) list over the ranks
         ia, fi, Ai, Qi = np.meshgrid(np.arange(na), refs['f'], refs['A'], refs['Q'], indexing='ij')
         ia, fi, Ai, Qi = [x.ravel() for x in (ia, fi, Ai, Qi)]
@@ -103,7 +108,12 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
         stats = {'n_points': n, 'n_rhs': int(nrhs.sum()), 'world_size': world}
     else:
         ndev = _lib.device_count()
-        mask = (1 << ndev) - 1 if (mpi and ndev > 1) else 1
+        if device is not None:
+            mask = 1 << int(device)
+        elif world > 1:
+            mask = 1 << local_rank
+        else:
+            mask = (1 << ndev) - 1 if (mpi and ndev > 1) else 1
         out, ncyc, status, tpoint, stats = _lib.lookup_run(
             bls_params, pneuron.neuron_id, nrates, refs['f'], refs['A'], refs['Q'], refs['fs'], mask)
     wall = time.perf_counter() - t0

@@ -222,23 +222,23 @@ def gen_c1(amp_scale=1.0, tag=''):
     _grid_to_npz(f'c1_RS_32nm_500kHz{tag}.npz', 'RS', [32e-9], [500e3], A, Q, [1.0], amp_scale)
 
 
-def gen_neurons():
+def gen_neurons(amp_scale=1.0, tag=''):
     ''' Small grids for the neurons of BASELINE configs 3-5. '''
     Aall = c2_amps()
     for name in ['FHnode', 'SWnode', 'MRGnode', 'SUseg']:
         Q = default_charges(name)
-        _grid_to_npz(f'c4_{name}_sub.npz', name, [32e-9], [100e3, 500e3, 4e6],
-                     Aall[[0, 20, 36, 44, 50]], Q[::max(1, Q.size // 6)], [1.0])
+        _grid_to_npz(f'c4_{name}_sub{tag}.npz', name, [32e-9], [100e3, 500e3, 4e6],
+                     Aall[[0, 20, 36, 44, 50]], Q[::max(1, Q.size // 6)], [1.0], amp_scale)
     for name in ['RE', 'TC']:
         pn = getPointNeuron(name)
         Qmin, Qmax = pn.Qbounds
         Q = np.arange(Qmin, Qmax + 5e-6, 5e-6)
         A = np.logspace(np.log10(50), np.log10(600), 26) * 1e3
-        _grid_to_npz(f'c5_{name}_sub.npz', name, [32e-9], [20e3, 500e3, 4e6],
-                     A[[0, 12, 25]], Q[::max(1, Q.size // 6)], [1.0])
+        _grid_to_npz(f'c5_{name}_sub{tag}.npz', name, [32e-9], [20e3, 500e3, 4e6],
+                     A[[0, 12, 25]], Q[::max(1, Q.size // 6)], [1.0], amp_scale)
     Q = default_charges('STN')
-    _grid_to_npz('c3_STN_sub.npz', 'STN', [32e-9], [500e3], Aall[[0, 16, 30, 40, 50]],
-                 Q[::24], np.arange(1, 101)[::11] * 1e-2)
+    _grid_to_npz(f'c3_STN_sub{tag}.npz', 'STN', [32e-9], [500e3], Aall[[0, 16, 30, 40, 50]],
+                 Q[::24], np.arange(1, 101)[::11] * 1e-2, amp_scale)
 
 
 def gen_c2sub(amp_scale=1.0, tag=''):
@@ -258,12 +258,16 @@ def gen_noise():
     gen_c1(dn, '_ulp_dn')
     gen_c2sub(up, '_ulp_up')
     gen_c2sub(dn, '_ulp_dn')
+    gen_neurons(up, '_ulp_up')
+    gen_neurons(dn, '_ulp_dn')
 
 
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
-            'c2sub': gen_c2sub, 'noise': gen_noise}
+            'c2sub': gen_c2sub, 'noise': gen_noise,
+            'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
+                                      gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what in (k, 'all'):
+        if what == k or (what == 'all' and k != 'noise_neurons'):
             fn()
