@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,9 +29,13 @@
 #include <vector>
 
 #define SONIC_BLOCK 128
+#ifndef SONIC_BLOCKS_PER_SM
+#define SONIC_BLOCKS_PER_SM 2      /* 3 (168 registers, 72 B of spills) measured slower: 2.71 s vs 2.37 s on C2 */
+#endif
 #define SONIC_HIST_STRIDE SONIC_BLOCK   /* per-lane indexed storage interleaved across the block */
 
 #include "../../include/sonic_b200.h"
+#include "generated/cost_table.h"
 #include "generated/neuron_rates.cuh"
 #include "sonic_core.h"
 
@@ -80,8 +85,11 @@ struct SonicJob {
     unsigned* nsteps;
     double* tpoint;
     unsigned long long* counter;
+    const int* warp_first;     // [warps]: first work-queue position of the warp's initial points
+    const int* warp_cap;       // [warps]: lanes of the warp allowed to work while those run
+    int* block_smid;           // [blocks]: SM each block ran on (placement probe / diagnostics)
     long long n;
-    int lanes_per_warp;
+    int probe;                 // 1 = record the block placement and return
 };
 
 __constant__ SonicTables c_tables;
@@ -103,7 +111,24 @@ __global__ void __launch_bounds__(128) sonic_z0_kernel(SonicJob job) {
     job.z0[i] = ok ? z0 : nan("");
 }
 
-__global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob job) {
+__global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integrate_kernel(SonicJob job) {
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        job.block_smid[blockIdx.x] = (int)smid;
+    }
+    if (job.probe) {
+        // keep every block resident until all have started, as in a real launch (bounded wait:
+        // the grid is one resident wave, but never spin forever on that assumption)
+        if (threadIdx.x == 0) {
+            atomicAdd(job.counter, 1ULL);
+            for (int spin = 0; spin < 200000; spin++) {
+                if (atomicAdd(job.counter, 0ULL) >= (unsigned long long)gridDim.x) break;
+                __nanosleep(200);
+            }
+        }
+        return;
+    }
     __shared__ SonicTables tab;
     {
         const double* src = reinterpret_cast<const double*>(&c_tables);
@@ -127,12 +152,26 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
     long long pt = -1;
     double period = 0.0;
     unsigned long long t_start = 0;
-    bool can_work = lane < job.lanes_per_warp;
+    // Lane budget of this warp.  The expensive points are long serial chains (up to 6e5 ticks):
+    // their wall time is chain length x tick latency, and the tick of a warp gets slower with
+    // every extra lane in a different integrator phase.  The host therefore hands the most
+    // expensive points out first, to warps that keep only `cap` lanes busy while those points
+    // run; once they are done the warp works at full width on whatever is left in the queue.
+    const int gwarp = (int)(slot >> 5);
+    int cap = job.warp_cap[gwarp];
+    long long q_init = (lane < cap) ? (long long)job.warp_first[gwarp] + lane : -1;
+    bool exhausted = false;
 
     while (true) {
-        if (pt < 0 && can_work) {
-            // refill this lane from the work queue
-            const unsigned long long q = atomicAdd(job.counter, 1ULL);
+        if (pt < 0 && !exhausted && lane < cap) {
+            // (re)fill this lane: its initial point first, then the shared work queue
+            unsigned long long q;
+            if (q_init >= 0) {
+                q = (unsigned long long)q_init;
+                q_init = -1;
+            } else {
+                q = atomicAdd(job.counter, 1ULL);
+            }
             if (q < (unsigned long long)job.n) {
                 pt = job.order[q];
                 const double f = job.f[pt];
@@ -152,16 +191,24 @@ __global__ void __launch_bounds__(SONIC_BLOCK) sonic_integrate_kernel(SonicJob j
                     sonic_lane_start(s, H, p, f, z0, sink);
                 }
             } else {
-                can_work = false;
+                exhausted = true;
             }
         }
         const bool active = pt >= 0;
-        if (!__any_sync(0xffffffffu, active || can_work)) break;
         const unsigned wmask = __ballot_sync(0xffffffffu, active);
+        if (wmask == 0u) {
+            // nothing running in this warp: widen it, or stop when the queue is drained
+            if (cap < 32) {
+                cap = 32;
+                continue;
+            }
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
         if (active) {
             double fv[3];
             if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-            sonic_tick(s, H, &tab, sink, period, fv, wmask);
+            sonic_tick(s, H, &tab, p, sink, period, fv, wmask);
             if (s.phase == PH_DONE) {
                 job.ncycles[pt] = s.cyc;
                 job.status[pt] = s.status;
@@ -301,13 +348,31 @@ static int check_device(int device) {
     return SONIC_OK;
 }
 
-// Predicted relative cost (log of RHS evaluations) of a point, used only to order the work
-// queue (longest first).  Least-squares fit on a stratified sample of the RS 4-D grid.
-static double predict_log_cost(double a, double f, double A) {
-    const double lf = log(f / 500e3), lA = log1p(A / 20e3), la = log(a / 32e-9);
-    const double noise = (A > 0. && A < 8e3) ? 1. : 0., zero = (A == 0.) ? 1. : 0.;
-    return 8.142 - 0.3655 * lf + 0.9828 * lA - 0.3437 * la + 0.2427 * noise - 0.534 * zero -
-           0.0237 * lf * lA - 0.1937 * noise * lf;
+// Predicted cost (log of right-hand-side evaluations) of a point, used only to order the work
+// queue (longest first) and to size the lane budgets: nearest node of a table measured on the
+// RS 4-D grid (generated/cost_table.h; the charge enters the mechanics through Q^2 only).
+static int nearest_log(const double* nodes, int n, double x) {
+    int best = 0;
+    double db = 1e300;
+    for (int i = 0; i < n; i++) {
+        const double dd = fabs(log(x / nodes[i]));
+        if (dd < db) { db = dd; best = i; }
+    }
+    return best;
+}
+
+static int bin_of(const double* edges, int nbins, double x) {
+    int j = 0;
+    while (j + 1 < nbins && x >= edges[j + 1]) j++;
+    return j;
+}
+
+static double predict_log_cost(double a, double f, double A, double Q) {
+    const int i = nearest_log(SONIC_COST_A, SONIC_COST_NA, a);
+    const int j = nearest_log(SONIC_COST_F, SONIC_COST_NF, f);
+    const int k = bin_of(SONIC_COST_AMP_EDGES, SONIC_COST_NAMP, A);
+    const int l = bin_of(SONIC_COST_Q_EDGES, SONIC_COST_NQ, fabs(Q) + 1e-14);
+    return SONIC_COST_LOG[((i * SONIC_COST_NF + j) * SONIC_COST_NAMP + k) * SONIC_COST_NQ + l];
 }
 
 struct SonicPlan {
@@ -318,6 +383,9 @@ struct SonicPlan {
     long long n = 0;
     long long slots = 0;
     int grid = 0, lanes_per_warp = 32;
+    unsigned long long n_initial = 0;   // work-queue positions handed out statically (counter start)
+    int *d_warp_first = nullptr, *d_warp_cap = nullptr, *d_block_smid = nullptr;
+    std::vector<int> probe_smid;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -345,7 +413,7 @@ static int plan_free(SonicPlan* p) {
     cudaFree(p->d_f); cudaFree(p->d_A); cudaFree(p->d_Q); cudaFree(p->d_fs); cudaFree(p->d_z0);
     cudaFree(p->d_zbuf); cudaFree(p->d_ngbuf); cudaFree(p->d_tpoint); cudaFree(p->d_out);
     cudaFree(p->d_status); cudaFree(p->d_nfe); cudaFree(p->d_nje); cudaFree(p->d_nsteps);
-    cudaFree(p->d_counter);
+    cudaFree(p->d_counter); cudaFree(p->d_warp_first); cudaFree(p->d_warp_cap); cudaFree(p->d_block_smid);
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
     if (p->stream && p->own_stream) cudaStreamDestroy(p->stream);
@@ -510,7 +578,7 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     std::vector<double> cost(n);
     for (int64_t i = 0; i < n; i++) {
         order[i] = (int)i;
-        cost[i] = predict_log_cost(radii[ia[i]].a, f[i], A[i]);
+        cost[i] = predict_log_cost(radii[ia[i]].a, f[i], A[i], Q[i]);
     }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
 
@@ -534,6 +602,60 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     TRYA(dalloc(&p->d_out, (size_t)(1 + p->nrates) * n * nfs));
     TRYA(dalloc(&p->d_status, n)); TRYA(dalloc(&p->d_nfe, n)); TRYA(dalloc(&p->d_nje, n));
     TRYA(dalloc(&p->d_nsteps, n)); TRYA(dalloc(&p->d_counter, 1));
+    const int warps_per_block = SONIC_BLOCK / 32;
+    const int nwarps = (int)blocks * warps_per_block;
+    TRYA(dalloc(&p->d_warp_first, nwarps)); TRYA(dalloc(&p->d_warp_cap, nwarps));
+    TRYA(dalloc(&p->d_block_smid, blocks));
+    // Placement probe: the same kernel, same launch configuration, returns after recording the
+    // SM of every block.  The persistent grid is exactly one resident wave, so the real launches
+    // land the same way; if they ever do not, only the schedule quality suffers, never the
+    // results (every point is still owned by exactly one warp).
+    std::vector<int> smid(blocks, 0);
+    if (e == cudaSuccess) {
+        SonicJob probe;
+        memset(&probe, 0, sizeof(probe));
+        probe.block_smid = p->d_block_smid;
+        probe.counter = p->d_counter;
+        probe.probe = 1;
+        TRYA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), p->stream));
+        sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
+        TRYA(cudaGetLastError());
+        TRYA(cudaMemcpyAsync(smid.data(), p->d_block_smid, blocks * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        TRYA(cudaStreamSynchronize(p->stream));
+    }
+    // Lane budgets (see the kernel).  Warps are walked SM by SM (all warps of all blocks of one
+    // SM, then the next SM), each taking the next `cap` points of the sorted list, so that the
+    // most expensive points end up alone in their warp on SMs that host nothing but such warps:
+    // a lone lane ticks in t1 = 2.3 us there, but in 3-4 us next to full, phase-diverged warps
+    // (instruction-cache and issue contention), and a warp with k busy lanes in about
+    //   t(k) = t1 (1 + GAIN (1 - exp(-(k - 1) / KDEC))),   t(32) = 2.55 t1.
+    // Every chain c should finish within (1 + MARGIN) c_max t1, so a warp whose most expensive
+    // point has predicted chain length c may run at t <= (1 + MARGIN) (c_max / c) t1.
+    std::vector<int> wfirst(nwarps, (int)n), wcap(nwarps, (int)lpw);
+    {
+        std::vector<int> border(blocks);
+        for (int b = 0; b < (int)blocks; b++) border[b] = b;
+        std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return smid[x] < smid[y]; });
+        const double GAIN = 1.55, KDEC = 2.5, MARGIN = 0.15;
+        const double cmax = cost[order[0]];
+        long long pos = 0;
+        for (int r = 0; r < nwarps; r++) {
+            const int gw = border[r / warps_per_block] * warps_per_block + r % warps_per_block;
+            if (pos >= n) continue;
+            const double ratio = exp(cmax - cost[order[pos]]);   // c_max / c (costs are logarithms)
+            const double x = ((1.0 + MARGIN) * ratio - 1.0) / GAIN;      // allowed slow-down / GAIN
+            const double k = x >= 0.98 ? 32.0 : 1.0 - KDEC * log(1.0 - x);
+            int cap = k >= (double)lpw ? (int)lpw : (int)k;
+            if (cap < 1) cap = 1;
+            wfirst[gw] = (int)pos;
+            wcap[gw] = cap;
+            pos += cap;
+        }
+        p->n_initial = (unsigned long long)(pos < n ? pos : n);
+        p->probe_smid = smid;
+    }
+    TRYA(cudaMemcpyAsync(p->d_warp_first, wfirst.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_warp_cap, wcap.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaMemcpyAsync(p->d_radii, hb.data(), na * sizeof(SonicBls), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaMemcpyAsync(p->d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaMemcpyAsync(p->d_ia, ia, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
@@ -561,8 +683,9 @@ int sonic_plan_launch(SonicPlan* p) {
     job.Q = p->d_Q; job.z0 = p->d_z0; job.zbuf = p->d_zbuf; job.ngbuf = p->d_ngbuf;
     job.ncycles = p->d_ncycles; job.status = p->d_status; job.nfe = p->d_nfe; job.nje = p->d_nje;
     job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
-    job.lanes_per_warp = p->lanes_per_warp;
-    CUDA_TRY(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), p->stream));
+    job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
+    job.block_smid = p->d_block_smid; job.probe = 0;
+    CUDA_TRY(cudaMemcpyAsync(p->d_counter, &p->n_initial, sizeof(p->n_initial), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(p->ev[1], p->stream));
@@ -647,6 +770,13 @@ int sonic_plan_stats(SonicPlan* p, SonicStats* st) {
     for (size_t i = 0; i < n; i++) {
         st->n_rhs += nfe[i]; st->n_jac += nje[i]; st->n_steps += nst[i]; st->n_cycles += ncyc[i];
     }
+    if (getenv("SONIC_DEBUG")) {
+        std::vector<int> now(p->grid);
+        CUDA_TRY(cudaMemcpy(now.data(), p->d_block_smid, p->grid * sizeof(int), cudaMemcpyDeviceToHost));
+        int diff = 0;
+        for (int b = 0; b < p->grid; b++) diff += now[b] != p->probe_smid[b];
+        fprintf(stderr, "[sonic] block placement: %d of %d blocks differ from the probe\n", diff, p->grid);
+    }
     st->n_points = n;
     st->n_launches = p->launches;
     st->ms_total = p->ms_upload;
@@ -717,7 +847,7 @@ int sonic_lookup_run(const SonicBlsParams* radii, int na, const double* f, int n
     std::vector<double> cost(n);
     for (int64_t k = 0; k < n; k++) {
         order[k] = (int)k;
-        cost[k] = predict_log_cost(radii[pia[k]].a, pf[k], pA[k]);
+        cost[k] = predict_log_cost(radii[pia[k]].a, pf[k], pA[k], pQ[k]);
     }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
     struct Shard {

@@ -205,26 +205,29 @@ SONIC_HD double sonic_ipow(double x, int k) {
     return r;
 }
 
-// d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).
+// d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).  The heuristics
+// only steer the step size (the result is clipped, thresholded at 10 % and multiplied by safety
+// factors), so on the device the power goes through the single-precision log2/exp2 units
+// (relative error ~1e-7), with the binary exponent of d split off in double precision so that
+// the whole double range is covered.  A dozen instructions instead of ~150, at seven call sites.
 SONIC_HD double sonic_powr(double d, double ex) {
 #if defined(__CUDA_ARCH__)
-    return exp(ex * log(d));
+    if (!(d > 0.0)) return 0.0;
+    const int hi = __double2hiint(d);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    const double m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(d));   // [1, 2)
+    const float l = (float)e + __log2f((float)m);
+    return (double)exp2f((float)ex * l);
 #else
     return pow(d, ex);
 #endif
 }
 
-// (d * c)^ex where log(d) may already be known (NaN = not yet) and lc = log(c) is tabulated:
-// on the device the logarithm of the local error estimate is computed once per step and shared
-// by every step-size candidate that is derived from it.
+// (d * c)^ex; `lc` = log(c) and `*ld` (a cache for log(d)) are kept for the host build's
+// signature only.
 SONIC_HD double sonic_powr_scaled(double d, double c, double lc, double ex, double* ld) {
-#if defined(__CUDA_ARCH__)
-    if (*ld != *ld) *ld = log(d);
-    return exp(ex * (*ld + lc));
-#else
     (void)lc; (void)ld;
-    return pow(d * c, ex);
-#endif
+    return sonic_powr(d * c, ex);
 }
 
 // Lennard-Jones intermolecular pressure (bls.py:29-41,472-480).
@@ -285,6 +288,33 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     dy[2] = SONIC_DIVC(2.0 * (SONIC_PI * s2) * SONIC_DGL * (SONIC_C0 - SONIC_DIVC(Pg, SONIC_KH)),
                        SONIC_XI);                                    // bls.py:508-516
     return clamped;
+}
+
+// Jacobian columns for the U and ng perturbations of a finite-difference Jacobian, as exact
+// differences f(y + r e_j) - f(y): the right-hand side is quadratic in U and linear in ng, so
+// the two differences only involve the viscous / inertial terms and the gas pressure and need
+// no transcendental function (same value as a full re-evaluation up to rounding).
+// d0[3] = f(U + rU, Z, ng) - f(U, Z, ng), d2[3] = f(U, Z, ng + rN) - f(U, Z, ng).
+SONIC_HD void sonic_rhs_diff_cols(const SonicPoint& p, const double y[3], double rU, double rN,
+                                  double d0[3], double d2[3]) {
+    const double U = y[0];
+    double Z = y[1];
+    if (Z < p.Zmin) Z = p.Zmin;
+    const double s2 = p.a2 + Z * Z;
+    const double inv_s2 = sonic_rcp(s2);
+    const double invR = 2.0 * Z * inv_s2;
+    const double ainvR = fabs(invR);
+    // dPv/dU (bls.py:613-631), then dU' = Ptot |1/R| / rhoL - 3 U^2 / (2 R) (bls.py:633-655)
+    const double dPv = -12.0 * SONIC_DELTA0 * SONIC_MUS * (invR * invR) - 4.0 * SONIC_MUL * ainvR;
+    d0[0] = SONIC_DIVC(rU * dPv * ainvR, SONIC_RHOL) - 1.5 * (rU * (2.0 * U + rU)) * invR;
+    d0[1] = rU;
+    d0[2] = 0.0;
+    // gas pressure is linear in ng (bls.py:518-526)
+    const double V = p.V0 * (1.0 + Z * p.c_vol * (3.0 + Z * Z * p.inva2));
+    const double dPg = rN * (SONIC_RG * SONIC_T) * sonic_rcp(V);
+    d2[0] = SONIC_DIVC(dPg * ainvR, SONIC_RHOL);
+    d2[1] = 0.0;
+    d2[2] = SONIC_DIVC(2.0 * (SONIC_PI * s2) * SONIC_DGL * (-SONIC_DIVC(dPg, SONIC_KH)), SONIC_XI);
 }
 
 // Quasi-static net pressure (bls.py:538-553).
@@ -372,7 +402,7 @@ enum SonicPhase : int {
     PH_INIT = 0,        // RHS at (t0, y0): first call of a fresh problem (one per cycle)
     PH_CORR_FIRST = 1,  // RHS at the predicted state (m = 0)
     PH_CORR_ITER = 2,   // RHS at a corrector iterate (m > 0)
-    PH_JAC = 3,         // RHS at a perturbed state (finite-difference Jacobian column)
+    PH_JAC = 3,         // RHS at the Z-perturbed state (finite-difference Jacobian, Z column)
     PH_RESET = 4,       // RHS at y_n after 3+ error-test failures (order reset)
     PH_DONE = 5
 };
@@ -418,7 +448,7 @@ struct SonicLane {
     int cyc, kout;
     unsigned status;
     // ---- statistics ----
-    unsigned nfe, nje, nsteps;
+    unsigned nfe, nje, nsteps;         // LSODA-equivalent counts (3 evaluations per Jacobian; full right-hand sides = nfe - 2 nje)
 #ifdef SONIC_TRACE
     double hu;
     int nqu;
@@ -464,7 +494,7 @@ SONIC_HD void sonic_set_order(SonicLane& s, const SonicTables* T) {
 // For jb = 1..nq the sweep updates columns nq-jb .. nq-1 (0-based) in ascending order.
 SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double sign) {
     const int nq = s.nq;
-    if (nq <= 5) {
+    if (sign > 0.0 && nq <= 5) {
         // Low orders (every BDF order): columns held in registers, top-aligned
         // (c[k] = column nq - k), so that sweep jb is "c[k] += c[k-1] for k = jb..1" whatever
         // the order; the same additions in the same order as the generic loop below.
@@ -499,7 +529,10 @@ SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double 
         }
         return;
     }
+    // generic form (orders > 5, and every retraction: rare, kept small)
+#pragma unroll 1
     for (int jb = 1; jb <= s.nq; jb++) {
+#pragma unroll 1
         for (int j = s.nq - jb; j < s.nq; j++) {
             H.yh(j, 0) += sign * H.yh(j + 1, 0);
             H.yh(j, 1) += sign * H.yh(j + 1, 1);
@@ -507,6 +540,14 @@ SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double 
         }
     }
 }
+
+// A pending step-size change: every place of the tick that decides one files it here and the
+// history is rescaled at a single site of the tick (one copy of the code instead of six).
+struct SonicRescaleReq {
+    bool pending;
+    bool rmax10;      // set rmax = 10 after the rescale (successful step)
+    double rh;
+};
 
 // Apply a step-size ratio: bound it, restrict by the Adams stability region, rescale history.
 SONIC_HD void sonic_rescale(SonicLane& s, const SonicHist& H, const SonicTables* T, double rh) {
@@ -711,7 +752,7 @@ SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepC
 }
 
 SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* T, double rhup,
-                           int iredo, SonicStepCtx* ctx) {
+                           int iredo, SonicStepCtx* ctx, SonicRescaleReq& rq) {
     const int l = s.nq + 1;
     const int lmax = SONIC_LMAX(s);
     double rhsm = sonic_rhsm0(s, T, ctx);
@@ -754,8 +795,7 @@ SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* 
         H.yh(l, 2) = s.acor[2] * r;
         s.nq = l;
         sonic_set_order(s, T);
-        sonic_rescale(s, H, T, rh);
-        if (iredo == 0) s.rmax = 10.0;
+        rq.pending = true; rq.rh = rh; rq.rmax10 = (iredo == 0);
         return iredo != 0;
     } else {
         newq = s.nq - 1;
@@ -774,15 +814,14 @@ SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* 
         s.nq = newq;
         sonic_set_order(s, T);
     }
-    sonic_rescale(s, H, T, rh);
-    if (iredo == 0) s.rmax = 10.0;
+    rq.pending = true; rq.rh = rh; rq.rmax10 = (iredo == 0);
     return iredo != 0;
 }
 
 // Consider switching Adams <-> BDF after a successful step.  Returns true if a switch was
 // made (history rescaled, step finished).
 SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicTables* T,
-                                  SonicStepCtx* ctx) {
+                                  SonicStepCtx* ctx, SonicRescaleReq& rq) {
     const double exsm = T->rk[s.nq + 1];
     if (s.meth == 1) {
         if (s.nq > 5) return false;
@@ -810,8 +849,7 @@ SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicT
         s.miter = 2;
         s.pdlast = 0.0;
         s.nq = nqm2;
-        sonic_rescale(s, H, T, rh2);
-        s.rmax = 10.0;
+        rq.pending = true; rq.rh = rh2; rq.rmax10 = true;
         return true;
     }
     // currently BDF (nq <= 5 <= MXORDN): consider Adams at the same order
@@ -835,30 +873,21 @@ SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicT
     s.miter = 0;
     s.pdlast = 0.0;
     s.nq = nqm1;
-    sonic_rescale(s, H, T, rh1);
-    s.rmax = 10.0;
+    rq.pending = true; rq.rh = rh1; rq.rmax10 = true;
     return true;
 }
 
-// Begin the finite-difference Jacobian column s.jcol: perturb that component of y.
-SONIC_HD void sonic_jac_perturb(SonicLane& s) {
-    const int j = s.jcol;
-    const double yj = (j == 0) ? s.y[0] : (j == 1) ? s.y[1] : s.y[2];
-    const double wj = (j == 0) ? s.ewt[0] : (j == 1) ? s.ewt[1] : s.ewt[2];
-    const double r = fmax(1.4901161193847656e-08 * fabs(yj), sonic_div(s.jac_r0, wj));
-    s.yj_save = yj;
-    const double yp = yj + r;
-    if (j == 0) s.y[0] = yp;
-    else if (j == 1) s.y[1] = yp;
-    else s.y[2] = yp;
+// Finite-difference increment of component j (LSODA: max(sqrt(uround) |y_j|, r0 / ewt_j)).
+SONIC_HD double sonic_jac_incr(const SonicLane& s, double yj, double wj) {
+    return fmax(1.4901161193847656e-08 * fabs(yj), sonic_div(s.jac_r0, wj));
 }
 
 // One tick: consume the RHS value `f` evaluated at (s.tn, s.y) and advance the lane to its
 // next evaluation point.  The body is a sequence of stages guarded by flags, so that lanes of
 // a warp that are in different phases still share every stage they have in common.
 SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
-                         const SonicSink& sink, double period, const double f[3],
-                         unsigned wmask) {
+                         const SonicPoint& p, const SonicSink& sink, double period,
+                         const double f[3], unsigned wmask) {
     (void)wmask;
     s.nfe++;
     bool do_corr = false;      // run the corrector update with savf
@@ -870,7 +899,9 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     if (s.phase == PH_CORR_FIRST || s.phase == PH_CORR_ITER) {
         s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
         if (s.phase == PH_CORR_FIRST && s.ipup > 0) {
-            // P = I - h el0 J must be re-evaluated: finite-difference Jacobian, 3 more ticks
+            // P = I - h el0 J must be re-evaluated: finite-difference Jacobian.  Only the Z column
+            // needs a full right-hand side (the next tick, at y + r_Z e_Z); the U and ng columns
+            // are exact differences of the terms that depend on them (sonic_rhs_diff_cols).
             s.nje++;
             s.ierpj = 0;
             s.jcur = 1;
@@ -878,29 +909,39 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
             double r0 = 1000.0 * fabs(s.h) * SONIC_UROUND * 3.0 * fac;
             if (r0 == 0.0) r0 = 1.0;
             s.jac_r0 = r0;
-            s.jcol = 0;
-            sonic_jac_perturb(s);
+            s.yj_save = s.y[1];
+            s.y[1] = s.yj_save + sonic_jac_incr(s, s.yj_save, s.ewt[1]);
             s.phase = PH_JAC;
         } else {
             if (s.phase == PH_CORR_FIRST) s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
             do_corr = true;
         }
     } else if (s.phase == PH_JAC) {
-        const int j = s.jcol;
-        const double wj = (j == 0) ? s.ewt[0] : (j == 1) ? s.ewt[1] : s.ewt[2];
-        const double rr = fmax(1.4901161193847656e-08 * fabs(s.yj_save), sonic_div(s.jac_r0, wj));
+        // f = RHS at (U, Z + r_Z, ng); LSODA counts three evaluations per Jacobian
+        s.nfe += 2;
         const double hl0 = s.h * s.el0;
-        const double fac = -sonic_div(hl0, rr);
-        H.wm(0 + 3 * j) = (f[0] - s.savf[0]) * fac;
-        H.wm(1 + 3 * j) = (f[1] - s.savf[1]) * fac;
-        H.wm(2 + 3 * j) = (f[2] - s.savf[2]) * fac;
-        if (j == 0) s.y[0] = s.yj_save;
-        else if (j == 1) s.y[1] = s.yj_save;
-        else s.y[2] = s.yj_save;
-        if (j < 2) {
-            s.jcol = j + 1;
-            sonic_jac_perturb(s);
-        } else {
+        {
+            const double rr = sonic_jac_incr(s, s.yj_save, s.ewt[1]);
+            const double fac = -sonic_div(hl0, rr);
+            H.wm(0 + 3) = (f[0] - s.savf[0]) * fac;
+            H.wm(1 + 3) = (f[1] - s.savf[1]) * fac;
+            H.wm(2 + 3) = (f[2] - s.savf[2]) * fac;
+            s.y[1] = s.yj_save;
+        }
+        {
+            const double r0u = sonic_jac_incr(s, s.y[0], s.ewt[0]);
+            const double r2n = sonic_jac_incr(s, s.y[2], s.ewt[2]);
+            // the increments actually applied by y_j + r in floating point
+            const double rU = (s.y[0] + r0u) - s.y[0];
+            const double rN = (s.y[2] + r2n) - s.y[2];
+            double d0[3], d2[3];
+            sonic_rhs_diff_cols(p, s.y, rU, rN, d0, d2);
+            const double fac0 = -sonic_div(hl0, r0u);
+            const double fac2 = -sonic_div(hl0, r2n);
+            H.wm(0) = d0[0] * fac0; H.wm(1) = d0[1] * fac0; H.wm(2) = d0[2] * fac0;
+            H.wm(6) = d2[0] * fac2; H.wm(7) = d2[1] * fac2; H.wm(8) = d2[2] * fac2;
+        }
+        {
             // norm of the Jacobian (matrix norm consistent with the weighted max-norm)
             double an = 0.0;
             double rew[3];
@@ -1046,6 +1087,8 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     double sel_rhup = 0.0;
     SonicStepCtx ctx;
     ctx.rhsm0 = ctx.lds = NAN;
+    SonicRescaleReq rq;
+    rq.pending = false; rq.rmax10 = false; rq.rh = 1.0;
     if (cf_retract || err_failed) {
         s.tn = s.told;
         sonic_pascal(s, H, -1.0);
@@ -1056,7 +1099,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                 sonic_fail(s, SONIC_ST_STEPFAIL);
             } else {
                 s.ipup = s.miter;
-                sonic_rescale(s, H, T, 0.25);
+                rq.pending = true; rq.rh = 0.25; rq.rmax10 = false;
                 do_predict = true;
             }
         } else {
@@ -1103,7 +1146,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     SONIC_STAGE_SYNC(wmask);
     // ---- stage C2: consider switching between the Adams and BDF families -----------------
     bool switched = false;
-    if (do_mswitch) switched = sonic_method_switch(s, H, T, &ctx);
+    if (do_mswitch) switched = sonic_method_switch(s, H, T, &ctx, rq);
 
     SONIC_STAGE_SYNC(wmask);
     // ---- stage C3: step/order bookkeeping after a success ---------------------------------
@@ -1131,11 +1174,18 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     SONIC_STAGE_SYNC(wmask);
     // ---- stage C4: order and step-size selection (after a success or a failed error test) -
     if (sel_mode != 0) {
-        const bool redo = sonic_select(s, H, T, sel_rhup, sel_mode == 2 ? 2 : 0, &ctx);
+        const bool redo = sonic_select(s, H, T, sel_rhup, sel_mode == 2 ? 2 : 0, &ctx, rq);
         if (sel_mode == 2) do_predict = true;
         (void)redo;
     }
     if (accepted && s.meth != s.mused) s.jstart = -1;   // method switch: reload coefficients
+
+    SONIC_STAGE_SYNC(wmask);
+    // ---- stage C5: the one place where the step size changes and the history is rescaled ----
+    if (rq.pending) {
+        sonic_rescale(s, H, T, rq.rh);
+        if (rq.rmax10) s.rmax = 10.0;
+    }
 
     SONIC_STAGE_SYNC(wmask);
     // ---- stage D: emit every output sample reached; end-of-cycle logic ------------------

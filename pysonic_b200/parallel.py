@@ -4,19 +4,39 @@
     to the ranks (every rank gets the same cost profile), each rank integrates its slab on its
     own device, and the per-point outputs are gathered once at the end. '''
 
+import json
 import os
 
 import numpy as np
 
 
-def predicted_log_cost(a, f, A):
-    ''' Same ordering heuristic as the native work queue (sonic_b200.cu: predict_log_cost). '''
-    a, f, A = np.asarray(a, float), np.asarray(f, float), np.asarray(A, float)
-    lf, lA, la = np.log(f / 500e3), np.log1p(A / 20e3), np.log(a / 32e-9)
-    noise = ((A > 0.) & (A < 8e3)).astype(float)
-    zero = (A == 0.).astype(float)
-    return (8.142 - 0.3655 * lf + 0.9828 * lA - 0.3437 * la + 0.2427 * noise - 0.534 * zero -
-            0.0237 * lf * lA - 0.1937 * noise * lf)
+_COST = None
+
+
+def _cost_table():
+    global _COST
+    if _COST is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'cost_table.json')
+        with open(path) as fh:
+            t = json.load(fh)
+        _COST = (np.log(np.array(t['a'])), np.log(np.array(t['f'])), np.array(t['A_edges_kPa']) * 1e3,
+                 np.array(t['absQ_edges_nCcm2']) * 1e-5, np.array(t['log_cost']))
+    return _COST
+
+
+def predicted_log_cost(a, f, A, Q=None):
+    ''' Same ordering heuristic as the native work queue (sonic_b200.cu: predict_log_cost):
+        nearest node of the measured cost table (tools/make_cost_table.py).  Without charges the
+        envelope over all charges is returned. '''
+    la, lf, Ae, Qe, tab = _cost_table()
+    a, f, A = np.broadcast_arrays(np.asarray(a, float), np.asarray(f, float), np.asarray(A, float))
+    i = np.argmin(np.abs(np.log(a)[..., None] - la), axis=-1)
+    j = np.argmin(np.abs(np.log(f)[..., None] - lf), axis=-1)
+    k = np.clip(np.digitize(A, Ae) - 1, 0, tab.shape[2] - 1)
+    if Q is None:
+        return tab.max(axis=3)[i, j, k]
+    l = np.clip(np.digitize(np.abs(np.asarray(Q, float)) + 1e-14, Qe) - 1, 0, tab.shape[3] - 1)
+    return tab[i, j, k, l]
 
 
 def dist_info():

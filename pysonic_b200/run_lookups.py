@@ -94,7 +94,7 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
         ia, fi, Ai, Qi = np.meshgrid(np.arange(na), refs['f'], refs['A'], refs['Q'], indexing='ij')
         ia, fi, Ai, Qi = [x.ravel() for x in (ia, fi, Ai, Qi)]
         n = ia.size
-        cost = predicted_log_cost(refs['a'][ia], fi, Ai)
+        cost = predicted_log_cost(refs['a'][ia], fi, Ai, Qi)
 
         def compute(idx):
             out, ncyc, status, tpoint, nrhs, st = _lib.points_run(

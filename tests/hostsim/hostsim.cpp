@@ -58,7 +58,7 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     while (s.phase != PH_DONE) {
         double fv[3];
         if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-        sonic_tick(s, H, &g_tab, sink, period, fv, 0u);
+        sonic_tick(s, H, &g_tab, p, sink, period, fv, 0u);
         nticks++;
         if (g_steplog && s.nsteps != last_nsteps && g_steplog_n < g_steplog_max) {
             double* r = g_steplog + 8 * g_steplog_n++;

@@ -84,6 +84,7 @@ def assert_grid_parity(tables, ncycles, golden, up, dn, keys, label=''):
     stable_nc = (up['ncycles'] == ref_nc) & (dn['ncycles'] == ref_nc)
     agree = ncycles == ref_nc
     self_agree = min(np.mean(up['ncycles'] == ref_nc), np.mean(dn['ncycles'] == ref_nc))
-    assert np.mean(agree) >= self_agree - 0.03, msg + f' | ncycles agreement {np.mean(agree):.4f} vs self {self_agree:.4f}'
-    assert np.mean(agree[stable_nc]) >= 0.97, msg + f' | ncycles agreement on stable points {np.mean(agree[stable_nc]):.4f}'
+    one = 1.01 / agree.size       # small grids: one point of slack (30-100 points per fixture)
+    assert np.mean(agree) >= self_agree - max(0.03, one), msg + f' | ncycles agreement {np.mean(agree):.4f} vs self {self_agree:.4f}'
+    assert np.mean(agree[stable_nc]) >= min(0.97, 1.0 - one * agree.size / max(stable_nc.sum(), 1)), msg + f' | ncycles agreement on stable points {np.mean(agree[stable_nc]):.4f}'
     return s_err, s_env, float(np.mean(agree)), float(self_agree)
