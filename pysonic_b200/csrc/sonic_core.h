@@ -25,6 +25,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SONIC_HD __host__ __device__ __forceinline__
@@ -113,6 +114,8 @@ struct SonicTables {
     double rk[16];    // 1 / k
     double c21[5];    // cm2[q] / cm1[q]
     double c12[5];    // cm1[q] / cm2[q]
+    double rtesco[2][12][3];   // 1 / tesco (0 where tesco is 0)
+    double rcon[2][12];        // 1 / (tesco[.][q][1] * conit(q)), conit(q) = 0.5 / (q + 2)
 };
 
 // Per-radius constants (one entry per sonophore radius of the lookup).
@@ -127,12 +130,12 @@ struct SonicBls {
 // Per-point constants derived once per lane.
 struct SonicPoint {
     double a, a2, inva2, inva, Delta, x0, Clj, nrep, nattr, Zmin;
-    double frep, fattr;        // fractional parts nrep - krep, nattr - kattr
-    int krep, kattr;           // nearest integers of the two Lennard-Jones exponents
+    double frep, fattr;        // nrep - 4, nattr - 1 (see sonic_pm)
     double V0, c_vol;          // V = V0 * (1 + Z * c_vol * (3 + Z^2 * inva2)), c_vol = 1/(3 Delta)
     double kAtot;              // kA + kA_tissue (N/m)
     double pel0;               // Q^2 / (2 eps0 epsR)
     double omega;              // 2 pi f
+    double f;
     double A;
     double ng0;
 };
@@ -147,18 +150,15 @@ SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, doubl
     p.Clj = b.C;
     p.nrep = b.nrep;
     p.nattr = b.nattr;
-    p.krep = (int)rint(b.nrep);
-    p.kattr = (int)rint(b.nattr);
-    if (p.krep < 0 || p.krep > 8) p.krep = 0;
-    if (p.kattr < 0 || p.kattr > 8) p.kattr = 0;
-    p.frep = b.nrep - p.krep;
-    p.fattr = b.nattr - p.kattr;
+    p.frep = b.nrep - 4.0;
+    p.fattr = b.nattr - 1.0;
     p.Zmin = SONIC_REL_ZMIN * b.Delta;
     p.V0 = SONIC_PI * b.Delta * p.a2;                   // bls.py:136
     p.c_vol = 1.0 / (3.0 * b.Delta);
     p.kAtot = SONIC_KA + 2.0 * (SONIC_ALPHA_TISSUE * f) * b.depth;   // bls.py:583-602
     p.pel0 = Q * Q / (2.0 * (SONIC_EPS0 * 1.0));        // bls.py:489-491
     p.omega = 2.0 * SONIC_PI * f;
+    p.f = f;
     p.A = A;
     p.ng0 = SONIC_P0 * p.V0 / (SONIC_RG * SONIC_T);     // bls.py:137,529-536
 }
@@ -189,20 +189,118 @@ SONIC_HD double sonic_div(double x, double y) {
 #endif
 }
 
-// x^k for a small non-negative integer k (binary powering, k <= 8).
-SONIC_HD double sonic_ipow(double x, int k) {
-    if (k == 4) {
-        const double x2 = x * x;
-        return x2 * x2;
-    }
-    if (k == 1) return x;
-    double r = (k & 1) ? x : 1.0;
-    const double x2 = x * x;
-    if (k & 2) r *= x2;
-    const double x4 = x2 * x2;
-    if (k & 4) r *= x4;
-    if (k & 8) r *= x4 * x4;
-    return r;
+// ---------------------------------------------------------------------------------------
+// Branch-free elementary functions for the right-hand side.
+//
+// The right-hand side is evaluated once per tick by every lane and sits on the serial critical
+// path of the expensive points, so its latency matters more than its instruction count.  The
+// library log / exp / sin carry special-case branches (denormals, huge arguments, infinities)
+// that split the RHS into many basic blocks and keep the compiler from interleaving its four
+// independent chains (intermolecular pressure, drive, curvature, gas pressure).  The arguments
+// here are known to be tame -- x = x0 / (2 Z + Delta) in [1e-2, 1e2], |(n - k) log x| < 5,
+// f t < 12 cycles -- so straight-line versions suffice: 1-2 ulp, no branches, polynomials in
+// Estrin form (dependent depth 4 instead of 13).
+// ---------------------------------------------------------------------------------------
+SONIC_HD int sonic_hiword(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u >> 32);
+#endif
+}
+
+SONIC_HD int sonic_loword(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)(u & 0xffffffffu);
+#endif
+}
+
+SONIC_HD double sonic_mkdouble(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+#endif
+}
+
+// Natural logarithm of a positive, finite, normal number.  Argument reduction and the
+// polynomial are the classical ones (x = 2^k m, m in [sqrt(1/2), sqrt(2)), s = f / (2 + f) with
+// f = m - 1, log(1 + f) = f - f^2/2 + s (f^2/2 + R(s^2)), R a degree-7 minimax polynomial).
+SONIC_HD double sonic_log(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int hx = sonic_hiword(x);
+    const int lx = sonic_loword(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;            // set when the mantissa exceeds sqrt(2)
+    const double m = sonic_mkdouble(hx | (i ^ 0x3ff00000), lx);
+    k += (i >> 20);
+    const double f = m - 1.0;
+    const double s = f * sonic_rcp(2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+}
+
+// Exponential for |x| < 700: x = k ln2 + r, |r| <= ln2 / 2, degree-13 Taylor polynomial of
+// exp(r) (truncation 4e-18) in Estrin form, scaled by 2^k through the exponent field.
+SONIC_HD double sonic_exp(double x) {
+    const double L2E = 1.4426950408889634074, ln2_hi = 6.93147180369123816490e-01,
+                 ln2_lo = 1.90821492927058770002e-10;
+    const double kf = rint(x * L2E);
+    double r = fma(-kf, ln2_hi, x);
+    r = fma(-kf, ln2_lo, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = 1.0 + r;
+    const double p23 = fma(r, 1.0 / 6.0, 0.5);
+    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
+    const double s0 = fma(r4, q1, q0), s1 = fma(r4, pcd, q2);
+    const double e = fma(r8, s1, s0);
+    return sonic_mkdouble(sonic_hiword(e) + ((int)kf << 20), sonic_loword(e));
+}
+
+// sin(2 pi u - pi) for u = f t >= 0 (drives.py:303-304 with phi = pi): -sin(2 pi r) with
+// r = u - rint(u) folded to [-1/4, 1/4], odd Taylor polynomial to theta^23 (truncation 5e-21).
+SONIC_HD double sonic_sin_drive(double u) {
+    double r = u - rint(u);
+    const double rf = copysign(0.5, r) - r;
+    r = (fabs(r) > 0.25) ? rf : r;
+    const double th = r * 6.283185307179586477;
+    const double z = th * th, z2 = z * z, z4 = z2 * z2;
+    // 1 - z/3! + z^2/5! - ... - z^11/23!
+    const double c01 = fma(z, -1.0 / 6.0, 1.0);
+    const double c23 = fma(z, -1.0 / 5040.0, 1.0 / 120.0);
+    const double c45 = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0);
+    const double c67 = fma(z, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    const double c89 = fma(z, -1.0 / 121645100408832000.0, 1.0 / 355687428096000.0);
+    const double cab = fma(z, -1.0 / 25852016738884976640000.0, 1.0 / 51090942171709440000.0);
+    const double d0 = fma(z2, c23, c01), d1 = fma(z2, c67, c45), d2 = fma(z2, cab, c89);
+    const double e0 = fma(z4, d1, d0);
+    const double poly = fma(z4 * z4, d2, e0);
+    return -(th * poly);
 }
 
 // d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).  The heuristics
@@ -231,19 +329,22 @@ SONIC_HD double sonic_powr_scaled(double d, double c, double lc, double ex, doub
 }
 
 // Lennard-Jones intermolecular pressure (bls.py:29-41,472-480).
-// x^n is evaluated as x^k * exp((n - k) log x) with k = rint(n): the two powers share one
-// logarithm and the exponential only carries the small fractional part, which keeps the result
-// within a few ulp of a correctly rounded pow at a third of its cost.
+// x^n is evaluated as x^k exp((n - k) log x) with k = 4 (repulsive) and k = 1 (attractive), the
+// integer parts of the fitted exponents (3.84-3.93 and 0-1.2 over the whole parameter table):
+// the two powers share one logarithm and the exponentials only carry the fractional parts,
+// which keeps the result within a few ulp of a correctly rounded pow at a third of its cost.
 SONIC_HD double sonic_pm(const SonicPoint& p, double Z) {
 #ifdef SONIC_EXACT_MATH
     const double xe = p.x0 / (2.0 * Z + p.Delta);
     return p.Clj * (pow(xe, p.nrep) - pow(xe, p.nattr));
-#endif
+#else
     const double x = p.x0 * sonic_rcp(2.0 * Z + p.Delta);
-    const double lx = log(x);
-    const double prep = sonic_ipow(x, p.krep) * exp(p.frep * lx);
-    const double pattr = sonic_ipow(x, p.kattr) * exp(p.fattr * lx);
+    const double lx = sonic_log(x);
+    const double x2 = x * x;
+    const double prep = (x2 * x2) * sonic_exp(p.frep * lx);
+    const double pattr = x * sonic_exp(p.fattr * lx);
     return p.Clj * (prep - pattr);
+#endif
 }
 
 // Gas pressure in the cavity (bls.py:311-319,518-526).
@@ -272,7 +373,11 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     const double ainvR = fabs(invR);
     const double Pg = sonic_pg(p, Z, ng);
     const double Pm = sonic_pm(p, Z);
+#ifdef SONIC_EXACT_MATH
     const double Pac = p.A * sin(p.omega * t - SONIC_PI);             // drives.py:303-304
+#else
+    const double Pac = p.A * sonic_sin_drive(p.f * t);
+#endif
     const double Pv = -12.0 * U * SONIC_DELTA0 * SONIC_MUS * (invR * invR)
                       - 4.0 * U * SONIC_MUL * ainvR;                  // bls.py:613-631
 #ifdef SONIC_EXACT_MATH
@@ -480,6 +585,8 @@ SONIC_HD void sonic_ewset(SonicLane& s, const SonicHist& H) {
 // coefficient accessors: l-vector of the current order in the currently loaded table
 #define SONIC_EL(s, T, j) ((T)->elco[(s).tab_meth - 1][(s).nq - 1][(j)])
 #define SONIC_TESCO(s, T, k) ((T)->tesco[(s).tab_meth - 1][(s).nq - 1][(k)])
+#define SONIC_RTESCO(s, T, k) ((T)->rtesco[(s).tab_meth - 1][(s).nq - 1][(k)])
+#define SONIC_RCON(s, T) ((T)->rcon[(s).tab_meth - 1][(s).nq - 1])
 #define SONIC_LMAX(s) ((s).tab_meth == 2 ? SONIC_MXORDS + 1 : SONIC_MXORDN + 1)
 
 // Reset the order-dependent constants (order nq of the loaded family).
@@ -560,8 +667,19 @@ SONIC_HD void sonic_rescale(SonicLane& s, const SonicHist& H, const SonicTables*
             s.irflag = 1;
         }
     }
+    // columns 1..5 with compile-time addresses (every BDF order), the rest (Adams > 5) in a loop
     double r = 1.0;
-    for (int j = 1; j <= s.nq; j++) {
+#pragma unroll
+    for (int j = 1; j <= 5; j++) {
+        r *= rh;
+        if (j <= s.nq) {
+            H.yh(j, 0) *= r;
+            H.yh(j, 1) *= r;
+            H.yh(j, 2) *= r;
+        }
+    }
+#pragma unroll 1
+    for (int j = 6; j <= s.nq; j++) {
         r *= rh;
         H.yh(j, 0) *= r;
         H.yh(j, 1) *= r;
@@ -639,6 +757,10 @@ SONIC_HD int sonic_lu3(const SonicHist& H, int* ipvt_packed) {
         }
     }
     if (a[8] == 0.0) info = 3;
+#if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
+    // the solves multiply by the reciprocal pivots (one factorisation serves several solves)
+    a[0] = sonic_rcp(a[0]); a[4] = sonic_rcp(a[4]); a[8] = sonic_rcp(a[8]);
+#endif
 #pragma unroll
     for (int k = 0; k < 9; k++) H.wm(k) = a[k];
     *ipvt_packed = piv;
@@ -665,7 +787,11 @@ SONIC_HD void sonic_lusolve3(const SonicHist& H, int ipvt_packed, double b[3]) {
     }
 #pragma unroll
     for (int k = 2; k >= 0; k--) {
-        b[k] = sonic_div(b[k], a[k + 3 * k]);
+#if defined(__CUDA_ARCH__) && !defined(SONIC_EXACT_MATH)
+        b[k] = b[k] * a[k + 3 * k];
+#else
+        b[k] = b[k] / a[k + 3 * k];
+#endif
         const double t = -b[k];
 #pragma unroll
         for (int i = 0; i < k; i++) b[i] += t * a[i + 3 * k];
@@ -675,9 +801,27 @@ SONIC_HD void sonic_lusolve3(const SonicHist& H, int ipvt_packed, double b[3]) {
 // Interpolate the solution at time t from the Nordsieck history (k = 0 derivative).
 SONIC_HD void sonic_interp(const SonicLane& s, const SonicHist& H, double t, double out[3]) {
     const double sfrac = sonic_div(t - s.tn, s.h);
+    const int nq = s.nq;
+    if (nq <= 5) {
+        // Horner from the top column down; columns above nq are skipped (compile-time addresses)
+        double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+#pragma unroll
+        for (int j = 5; j >= 0; j--) {
+            if (j == nq) {
+                o0 = H.yh(j, 0); o1 = H.yh(j, 1); o2 = H.yh(j, 2);
+            } else if (j < nq) {
+                o0 = H.yh(j, 0) + sfrac * o0;
+                o1 = H.yh(j, 1) + sfrac * o1;
+                o2 = H.yh(j, 2) + sfrac * o2;
+            }
+        }
+        out[0] = o0; out[1] = o1; out[2] = o2;
+        return;
+    }
     out[0] = H.yh(s.nq, 0);
     out[1] = H.yh(s.nq, 1);
     out[2] = H.yh(s.nq, 2);
+#pragma unroll 1
     for (int j = s.nq - 1; j >= 0; j--) {
         out[0] = H.yh(j, 0) + sfrac * out[0];
         out[1] = H.yh(j, 1) + sfrac * out[1];
@@ -758,7 +902,7 @@ SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* 
     double rhsm = sonic_rhsm0(s, T, ctx);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = sonic_div(sonic_mnorm_col(H, s.nq, s.ewt), SONIC_TESCO(s, T, 0));
+        const double ddn = SONIC_QUOT(sonic_mnorm_col(H, s.nq, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
         const double exdn = T->rk[s.nq];
         rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn) + 0.0000013);
     }
@@ -1039,7 +1183,10 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                 s.rate = fmax(s.rate, rm);
                 s.crate = fmax(0.2 * s.crate, rm);
             }
-            const double dcon = sonic_div(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit);
+#ifdef SONIC_CHECK_TABLES
+            if (fabs(SONIC_RCON(s, T) * (SONIC_TESCO(s, T, 1) * s.conit) - 1.0) > 1e-12) abort();
+#endif
+            const double dcon = SONIC_QUOT(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit, SONIC_RCON(s, T));
             if (dcon <= 1.0) {
                 s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));
                 if (s.pdest != 0.0) s.pdlast = s.pdest;
@@ -1063,8 +1210,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     bool err_failed = false;
     if (converged) {
         s.jcur = 0;
-        const double tq2 = SONIC_TESCO(s, T, 1);
-        s.dsm = sonic_div((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), tq2);
+        s.dsm = SONIC_QUOT((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), SONIC_TESCO(s, T, 1), SONIC_RTESCO(s, T, 1));
         err_failed = s.dsm > 1.0;
     }
     bool cf_retract = false;
@@ -1133,11 +1279,24 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         s.nqu = s.nq;
 #endif
         s.mused = s.meth;
-        for (int j = 0; j <= s.nq; j++) {
-            const double e = SONIC_EL(s, T, j);
-            H.yh(j, 0) += e * s.acor[0];
-            H.yh(j, 1) += e * s.acor[1];
-            H.yh(j, 2) += e * s.acor[2];
+        {
+            const double* el = &SONIC_EL(s, T, 0);
+#pragma unroll
+            for (int j = 0; j <= 5; j++) {
+                if (j <= s.nq) {
+                    const double e = el[j];
+                    H.yh(j, 0) += e * s.acor[0];
+                    H.yh(j, 1) += e * s.acor[1];
+                    H.yh(j, 2) += e * s.acor[2];
+                }
+            }
+#pragma unroll 1
+            for (int j = 6; j <= s.nq; j++) {
+                const double e = el[j];
+                H.yh(j, 0) += e * s.acor[0];
+                H.yh(j, 1) += e * s.acor[1];
+                H.yh(j, 2) += e * s.acor[2];
+            }
         }
         s.icount--;
         do_mswitch = s.icount < 0;
@@ -1159,7 +1318,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                 const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
                                                 s.acor[1] - H.yh(lmax - 1, 1),
                                                 s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
-                const double dup = sonic_div(dup0, SONIC_TESCO(s, T, 2));
+                const double dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
                 const double exup = T->rk[l + 1];
                 sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
             }
@@ -1413,5 +1572,11 @@ static void sonic_fill_tables(SonicTables* T) {
     }
     T->rk[0] = 0.0;
     for (int i = 1; i < 16; i++) T->rk[i] = 1.0 / i;
+    for (int m = 0; m < 2; m++)
+        for (int q = 0; q < 12; q++) {
+            for (int k = 0; k < 3; k++) T->rtesco[m][q][k] = T->tesco[m][q][k] != 0.0 ? 1.0 / T->tesco[m][q][k] : 0.0;
+            const double den = T->tesco[m][q][1] * (0.5 / (q + 3));
+            T->rcon[m][q] = den != 0.0 ? 1.0 / den : 0.0;
+        }
 }
 

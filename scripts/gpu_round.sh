@@ -25,6 +25,6 @@ if [ "${NO_NCU:-0}" = "0" ]; then
   CMD2="python bench.py --steps 1 --warmup 0 --no-cpu-baseline"
   $CMD2 > $OUT/plain_c2_$TAG.log 2>&1 && \
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_active.avg,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,gpu__time_duration.sum \
-      --clock-control none -k regex:sonic_integrate -c 1 --csv --log-file $OUT/c2_counters_$TAG.csv $CMD2 > $OUT/ncu_c2_$TAG.log 2>&1
+      --clock-control none -k regex:sonic_integrate -s 1 -c 1 --csv --log-file $OUT/c2_counters_$TAG.csv $CMD2 > $OUT/ncu_c2_$TAG.log 2>&1
   echo "ncu c2 counters rc=$?"
 fi

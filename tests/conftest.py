@@ -94,8 +94,8 @@ class HostSim:
                                    ctypes.c_double(A), ctypes.c_double(Q))
 
     def tables(self):
-        n = 2 * 12 * 13 + 2 * 12 * 3 + 12 + 5 + 12 + 5 + 16 + 5 + 5
-        buf = np.zeros(n)
+        self.lib.hostsim_tables_size.restype = ctypes.c_long
+        buf = np.zeros(self.lib.hostsim_tables_size())
         self.lib.hostsim_tables(buf.ctypes.data_as(self.dp))
         return {'elco': buf[:312].reshape(2, 12, 13), 'tesco': buf[312:384].reshape(2, 12, 3),
                 'cm1': buf[384:396], 'cm2': buf[396:401], 'sm1': buf[401:413]}

@@ -90,6 +90,13 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     return nticks;
 }
 
+// elementwise check of the branch-free elementary functions of the right-hand side
+// kind 0: log, 1: exp, 2: sin(2 pi u - pi), 3: reciprocal
+void hostsim_math(int kind, const double* x, double* out, long n) {
+    for (long i = 0; i < n; i++)
+        out[i] = kind == 0 ? sonic_log(x[i]) : kind == 1 ? sonic_exp(x[i]) : kind == 2 ? sonic_sin_drive(x[i]) : sonic_rcp(x[i]);
+}
+
 void hostsim_rhs(const double* bls, double f, double A, double Q, double t, const double* y,
                  double* dy) {
     SonicBls b;
@@ -110,6 +117,8 @@ double hostsim_z0(const double* bls, double f, double A, double Q) {
     sonic_z0(p, f, &z0);
     return z0;
 }
+
+long hostsim_tables_size(void) { return (long)(sizeof(SonicTables) / sizeof(double)); }
 
 void hostsim_tables(double* out) {
     if (!g_tab_ready) {
