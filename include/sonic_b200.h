@@ -139,6 +139,10 @@ int sonic_plan_fetch_zprofiles(SonicPlan* plan, double* out_z);
 int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
 int sonic_plan_destroy(SonicPlan* plan);
 
+/* Releases the device workspace that one-shot calls keep between invocations (the cycle-profile
+ * buffers, up to 8 kB per point): call it when no further lookup will be generated. */
+int sonic_trim(void);
+
 /* Sustained FP64 FMA throughput of the device (TFLOP/s), measured with a register-resident
  * DFMA kernel: the roofline denominator for the integrator. */
 int sonic_fp64_peak(int device, double* tflops);

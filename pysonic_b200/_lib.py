@@ -62,6 +62,7 @@ EXPORTS = {
     'sonic_plan_fetch_zprofiles': (C.c_int, [C.c_void_p, _dp]),
     'sonic_plan_stats': (C.c_int, [C.c_void_p, _sp]),
     'sonic_plan_destroy': (C.c_int, [C.c_void_p]),
+    'sonic_trim': (C.c_int, []),
     'sonic_fp64_peak': (C.c_int, [C.c_int, _dp]),
 }
 
@@ -143,6 +144,11 @@ def eval_mean_rates(pneuron, Vm, device=0):
     out = np.empty(nr)
     check(lib.sonic_mean_rates(device, pneuron.neuron_id, _d(Vm), Vm.size, _d(out)))
     return {k: float(out[i]) for i, k in enumerate(pneuron.rates)}
+
+
+def trim():
+    ''' Release the device workspace kept between one-shot calls. '''
+    check(load().sonic_trim())
 
 
 def fp64_peak(device=0):

@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -352,13 +353,11 @@ static int check_device(int device) {
 // queue (longest first) and to size the lane budgets: nearest node of a table measured on the
 // RS 4-D grid (generated/cost_table.h; the charge enters the mechanics through Q^2 only).
 static int nearest_log(const double* nodes, int n, double x) {
-    int best = 0;
-    double db = 1e300;
-    for (int i = 0; i < n; i++) {
-        const double dd = fabs(log(x / nodes[i]));
-        if (dd < db) { db = dd; best = i; }
-    }
-    return best;
+    // nearest node on a logarithmic axis = first node whose geometric midpoint with the next
+    // one lies above x (nodes ascending)
+    int i = 0;
+    while (i + 1 < n && x * x > nodes[i] * nodes[i + 1]) i++;
+    return i;
 }
 
 static int bin_of(const double* edges, int nbins, double x) {
@@ -375,6 +374,47 @@ static double predict_log_cost(double a, double f, double A, double Q) {
     return SONIC_COST_LOG[((i * SONIC_COST_NF + j) * SONIC_COST_NAMP + k) * SONIC_COST_NQ + l];
 }
 
+// ---------------------------------------------------------------------------------------
+// Workspace pool: the two large per-plan buffers (cycle profiles) are kept per device between
+// calls, so that repeated one-shot calls (sonic_points_run / sonic_lookup_run) do not pay a
+// multi-GB cudaMalloc / cudaFree every time.  sonic_trim() releases them.
+// ---------------------------------------------------------------------------------------
+struct PoolSlot {
+    double* ptr = nullptr;
+    size_t count = 0;
+};
+static std::mutex g_pool_mutex;
+static PoolSlot g_pool[64][2];   // [device][0 = zbuf, 1 = ngbuf]
+
+static cudaError_t pool_take(int device, int which, size_t count, double** out) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        PoolSlot& sl = g_pool[device & 63][which];
+        if (sl.ptr && sl.count >= count) {
+            *out = sl.ptr;
+            sl.ptr = nullptr;
+            sl.count = 0;
+            return cudaSuccess;
+        }
+    }
+    return cudaMalloc(reinterpret_cast<void**>(out), std::max<size_t>(count, 1) * sizeof(double));
+}
+
+static void pool_give(int device, int which, double* ptr, size_t count) {
+    if (!ptr) return;
+    double* drop = ptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mutex);
+        PoolSlot& sl = g_pool[device & 63][which];
+        if (!sl.ptr || sl.count < count) {
+            drop = sl.ptr;
+            sl.ptr = ptr;
+            sl.count = count;
+        }
+    }
+    if (drop) cudaFree(drop);
+}
+
 struct SonicPlan {
     int device = 0;
     int neuron_id = 0;
@@ -383,6 +423,7 @@ struct SonicPlan {
     long long n = 0;
     long long slots = 0;
     int grid = 0, lanes_per_warp = 32;
+    size_t zbuf_count = 0, ngbuf_count = 0;
     unsigned long long n_initial = 0;   // work-queue positions handed out statically (counter start)
     int *d_warp_first = nullptr, *d_warp_cap = nullptr, *d_block_smid = nullptr;
     std::vector<int> probe_smid;
@@ -411,7 +452,8 @@ static int plan_free(SonicPlan* p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_radii); cudaFree(p->d_order); cudaFree(p->d_ia); cudaFree(p->d_ncycles);
     cudaFree(p->d_f); cudaFree(p->d_A); cudaFree(p->d_Q); cudaFree(p->d_fs); cudaFree(p->d_z0);
-    cudaFree(p->d_zbuf); cudaFree(p->d_ngbuf); cudaFree(p->d_tpoint); cudaFree(p->d_out);
+    pool_give(p->device, 0, p->d_zbuf, p->zbuf_count); pool_give(p->device, 1, p->d_ngbuf, p->ngbuf_count);
+    cudaFree(p->d_tpoint); cudaFree(p->d_out);
     cudaFree(p->d_status); cudaFree(p->d_nfe); cudaFree(p->d_nje); cudaFree(p->d_nsteps);
     cudaFree(p->d_counter); cudaFree(p->d_warp_first); cudaFree(p->d_warp_cap); cudaFree(p->d_block_smid);
     for (auto& e : p->ev)
@@ -596,8 +638,10 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     TRYA(dalloc(&p->d_order, n)); TRYA(dalloc(&p->d_ia, n)); TRYA(dalloc(&p->d_ncycles, n));
     TRYA(dalloc(&p->d_f, n)); TRYA(dalloc(&p->d_A, n)); TRYA(dalloc(&p->d_Q, n));
     TRYA(dalloc(&p->d_fs, nfs)); TRYA(dalloc(&p->d_z0, n));
-    TRYA(dalloc(&p->d_zbuf, (size_t)n * SONIC_NPC));
-    TRYA(dalloc(&p->d_ngbuf, (size_t)p->slots * SONIC_NPC));
+    p->zbuf_count = (size_t)n * SONIC_NPC;
+    p->ngbuf_count = (size_t)p->slots * SONIC_NPC;
+    TRYA(pool_take(device, 0, p->zbuf_count, &p->d_zbuf));
+    TRYA(pool_take(device, 1, p->ngbuf_count, &p->d_ngbuf));
     TRYA(dalloc(&p->d_tpoint, n));
     TRYA(dalloc(&p->d_out, (size_t)(1 + p->nrates) * n * nfs));
     TRYA(dalloc(&p->d_status, n)); TRYA(dalloc(&p->d_nfe, n)); TRYA(dalloc(&p->d_nje, n));
@@ -790,16 +834,25 @@ int sonic_points_run(int device, const SonicBlsParams* radii, int na, int neuron
                      const double* fs, int nfs, double* out_tables, int32_t* out_ncycles,
                      uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats) {
     const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     SonicPlan* p = nullptr;
     int rc = sonic_plan_create(device, radii, na, neuron_id, n, ia, f, A, Q, fs, nfs, &p);
     if (rc) return rc;
+    const double ms_create = ms_since(t0);
     rc = sonic_plan_launch(p);
     if (!rc) rc = sonic_plan_fetch(p, out_tables, out_ncycles, out_status, out_tpoint, out_nrhs);
+    const double ms_run = ms_since(t0) - ms_create;
     if (!rc && stats) {
         rc = sonic_plan_stats(p, stats);
-        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->ms_total = ms_since(t0);
     }
+    const double ms_stats = ms_since(t0) - ms_create - ms_run;
     plan_free(p);
+    if (getenv("SONIC_DEBUG"))
+        fprintf(stderr, "[sonic] points_run n=%lld: create %.1f ms, launch+fetch %.1f ms, stats %.1f ms, free %.1f ms\n",
+                (long long)n, ms_create, ms_run, ms_stats, ms_since(t0) - ms_create - ms_run - ms_stats);
     return rc;
 }
 
@@ -906,6 +959,26 @@ int sonic_lookup_run(const SonicBlsParams* radii, int na, const double* f, int n
     }
     tot.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = tot;
+    return SONIC_OK;
+}
+
+int sonic_trim(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return SONIC_OK;
+    for (int d = 0; d < ndev && d < 64; d++)
+        for (int w = 0; w < 2; w++) {
+            double* ptr = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(g_pool_mutex);
+                ptr = g_pool[d][w].ptr;
+                g_pool[d][w].ptr = nullptr;
+                g_pool[d][w].count = 0;
+            }
+            if (ptr) {
+                cudaSetDevice(d);
+                cudaFree(ptr);
+            }
+        }
     return SONIC_OK;
 }
 

@@ -85,13 +85,15 @@ def gather_slabs(n, idx, arrays, rank, world_size):
         arr = np.moveaxis(np.asarray(arr), axis, 0)
         pad = np.zeros((mmax,) + arr.shape[1:], dtype=arr.dtype)
         pad[:m] = arr
-        t = torch.from_numpy(np.ascontiguousarray(pad)).to(dev)
+        # ship raw bytes: NCCL has no unsigned 32-bit type (status words, RHS counts)
+        t = torch.from_numpy(np.ascontiguousarray(pad).view(np.uint8).reshape(-1)).to(dev)
         parts = [torch.zeros_like(t) for _ in range(world_size)]
         dist.all_gather(parts, t)
         full = np.zeros((n,) + arr.shape[1:], dtype=arr.dtype)
         for r in range(world_size):
             k = sizes[r]
-            full[all_idx[r][:k]] = parts[r].cpu().numpy()[:k]
+            part = parts[r].cpu().numpy().view(arr.dtype).reshape(pad.shape)
+            full[all_idx[r][:k]] = part[:k]
         out.append(np.moveaxis(full, 0, axis))
     return out
 

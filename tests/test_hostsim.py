@@ -61,6 +61,35 @@ def test_rhs_matches_oracle(hostsim):
                                hostsim.rhs(b, 5e5, 1e5, -7e-4, 1e-7, [0.01, b.Zmin, b.ng0]), rtol=0)
 
 
+def test_rhs_elementary_functions(hostsim):
+    ''' The branch-free log / exp / sin of the right-hand side (sonic_core.h) over their argument
+        ranges: 1-2 ulp against libm, the drive phase against an exact reduction. '''
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def call(kind, x):
+        x = np.ascontiguousarray(x, float)
+        out = np.empty_like(x)
+        hostsim.lib.hostsim_math(ctypes.c_int(kind), x.ctypes.data_as(dp), out.ctypes.data_as(dp),
+                                 ctypes.c_long(x.size))
+        return out
+
+    rng = np.random.default_rng(0)
+    ulp = lambda a, b: np.abs(a - b) / np.spacing(np.abs(b))   # noqa: E731
+    x = np.concatenate([10 ** rng.uniform(-4, 4, 100000), rng.uniform(0.7, 1.5, 50000)])
+    assert ulp(call(0, x), np.log(x))[x != 1.0].max() <= 1.5
+    assert call(0, np.array([1.0]))[0] == 0.0
+    x = rng.uniform(-8, 8, 100000)
+    assert ulp(call(1, x), np.exp(x)).max() <= 2.5
+    assert call(1, np.array([0.0]))[0] == 1.0
+    # sin(2 pi u - pi) with u = f t up to 12 cycles: exact reduction in long double
+    u = rng.uniform(0, 12, 100000)
+    ul = u.astype(np.longdouble)
+    ref = -np.sin(2 * np.pi * (ul - np.round(ul)).astype(float))      # |r| <= 1/2: argument exact to 1 ulp
+    assert np.max(np.abs(call(2, u) - ref)) <= 1e-15
+    for uu, v in ((0.0, 0.0), (0.25, -1.0), (0.5, 0.0), (0.75, 1.0), (3.25, -1.0)):
+        assert call(2, np.array([uu]))[0] == pytest.approx(v, abs=1e-15)
+
+
 def test_initial_deflection(hostsim, points_golden):
     for r in points_golden['Z0']:
         b = so.get_bls(r['neuron'], r['a'])

@@ -23,7 +23,8 @@ def _fake_compute(a, f, A, Q, fs):
     out = np.stack([np.outer(base * (v + 1), fs) for v in range(3)])       # (3, n, nfs)
     ncyc = (3 + (A == 0) * 8).astype(np.int32)
     tpoint = base * 1e-3
-    return out, ncyc, tpoint
+    status = (A == 0).astype(np.uint32)
+    return out, ncyc, tpoint, status
 
 
 def _worker(rank, world, port, n, ret):
@@ -38,11 +39,11 @@ def _worker(rank, world, port, n, ret):
         cost = predicted_log_cost(a, f, A)
 
         def compute(idx):
-            out, ncyc, tp = _fake_compute(a[idx], f[idx], A[idx], Q[idx], fs)
-            return [(out, 1), (ncyc, 0), (tp, 0)]
+            out, ncyc, tp, st = _fake_compute(a[idx], f[idx], A[idx], Q[idx], fs)
+            return [(out, 1), (ncyc, 0), (tp, 0), (st, 0)]
 
-        out, ncyc, tp = run_sharded(compute, n, cost)
-        ret[rank] = (out, ncyc, tp)
+        out, ncyc, tp, st = run_sharded(compute, n, cost)
+        ret[rank] = (out, ncyc, tp, st)
     finally:
         dist.destroy_process_group()
 
@@ -70,9 +71,11 @@ def test_two_rank_gather_matches_single_process(n):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n, ret), nprocs=world, join=True)
     a, f, A, Q, fs = _inputs(n)
-    ref_out, ref_ncyc, ref_tp = _fake_compute(a, f, A, Q, fs)
+    ref_out, ref_ncyc, ref_tp, ref_st = _fake_compute(a, f, A, Q, fs)
     for r in range(world):
-        out, ncyc, tp = ret[r]
+        out, ncyc, tp, st = ret[r]
+        np.testing.assert_array_equal(st, ref_st)
+        assert st.dtype == np.uint32
         np.testing.assert_array_equal(out, ref_out)
         np.testing.assert_array_equal(ncyc, ref_ncyc)
         np.testing.assert_array_equal(tp, ref_tp)
@@ -86,7 +89,7 @@ def test_single_process_path():
     a, f, A, Q, fs = _inputs(n)
 
     def compute(idx):
-        out, ncyc, tp = _fake_compute(a[idx], f[idx], A[idx], Q[idx], fs)
+        out, ncyc, tp, st = _fake_compute(a[idx], f[idx], A[idx], Q[idx], fs)
         return [(out, 1), (ncyc, 0), (tp, 0)]
 
     out, ncyc, tp = run_sharded(compute, n, predicted_log_cost(a, f, A))
