@@ -426,7 +426,7 @@ struct SonicPlan {
     size_t zbuf_count = 0, ngbuf_count = 0;
     unsigned long long n_initial = 0;   // work-queue positions handed out statically (counter start)
     int *d_warp_first = nullptr, *d_warp_cap = nullptr, *d_block_smid = nullptr;
-    std::vector<int> probe_smid;
+    std::vector<int> probe_smid, last_smid;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -650,6 +650,13 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     const int nwarps = (int)blocks * warps_per_block;
     TRYA(dalloc(&p->d_warp_first, nwarps)); TRYA(dalloc(&p->d_warp_cap, nwarps));
     TRYA(dalloc(&p->d_block_smid, blocks));
+    TRYA(cudaMemcpyAsync(p->d_radii, hb.data(), na * sizeof(SonicBls), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_ia, ia, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_f, f, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_A, A, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_Q, Q, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    TRYA(cudaMemcpyAsync(p->d_fs, fs, nfs * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     // Placement probe: the same kernel, same launch configuration, returns after recording the
     // SM of every block.  The persistent grid is exactly one resident wave, so the real launches
     // land the same way; if they ever do not, only the schedule quality suffers, never the
@@ -662,6 +669,15 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
         probe.counter = p->d_counter;
         probe.probe = 1;
         TRYA(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned long long), p->stream));
+        // same launch sequence as sonic_plan_launch (the initial-deflection kernel right before):
+        // where its last blocks retire decides which SMs take the first integrator blocks
+        {
+            SonicJob zj;
+            memset(&zj, 0, sizeof(zj));
+            zj.radii = p->d_radii; zj.ia = p->d_ia; zj.f = p->d_f; zj.A = p->d_A; zj.Q = p->d_Q;
+            zj.z0 = p->d_z0; zj.n = p->n;
+            sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(zj);
+        }
         sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
         TRYA(cudaGetLastError());
         TRYA(cudaMemcpyAsync(smid.data(), p->d_block_smid, blocks * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
@@ -700,13 +716,6 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     }
     TRYA(cudaMemcpyAsync(p->d_warp_first, wfirst.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaMemcpyAsync(p->d_warp_cap, wcap.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_radii, hb.data(), na * sizeof(SonicBls), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_ia, ia, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_f, f, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_A, A, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_Q, Q, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    TRYA(cudaMemcpyAsync(p->d_fs, fs, nfs * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaStreamSynchronize(p->stream));
 #undef TRYA
     if (e != cudaSuccess) {
@@ -729,6 +738,24 @@ int sonic_plan_launch(SonicPlan* p) {
     job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
     job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
     job.block_smid = p->d_block_smid; job.probe = 0;
+    if (getenv("SONIC_DEBUG") && p->launched) {
+        // placement of the previous launch against the probe (and the launch before)
+        std::vector<int> now(p->grid);
+        CUDA_TRY(cudaMemcpy(now.data(), p->d_block_smid, p->grid * sizeof(int), cudaMemcpyDeviceToHost));
+        int d_probe = 0, d_prev = 0, same_sm_set = 0;
+        for (int b = 0; b < p->grid; b++) {
+            d_probe += now[b] != p->probe_smid[b];
+            if (!p->last_smid.empty()) d_prev += now[b] != p->last_smid[b];
+        }
+        fprintf(stderr, "[sonic] placement of last launch: %d of %d blocks differ from the probe, %d from the launch before\n",
+                d_probe, p->grid, d_prev);
+        for (int b = 0; b < p->grid && same_sm_set < 12; b++)
+            if (now[b] != p->probe_smid[b]) {
+                fprintf(stderr, "    block %d: probe SM %d, real SM %d\n", b, p->probe_smid[b], now[b]);
+                same_sm_set++;
+            }
+        p->last_smid = now;
+    }
     CUDA_TRY(cudaMemcpyAsync(p->d_counter, &p->n_initial, sizeof(p->n_initial), cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaEventRecord(p->ev[0], p->stream));
     sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);
