@@ -696,23 +696,53 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
         std::vector<int> border(blocks);
         for (int b = 0; b < (int)blocks; b++) border[b] = b;
         std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return smid[x] < smid[y]; });
-        const double GAIN = 1.55, KDEC = 2.5, MARGIN = 0.15;
-        const double cmax = cost[order[0]];
+        const double GAIN = 1.55, KDEC = 2.5, T32 = 1.0 + GAIN;       // t(k) / t1, t(32) / t1
+        std::vector<double> chain(n), tail(n + 1, 0.0);               // predicted ticks, suffix sums
+        for (long long i = 0; i < n; i++) chain[i] = exp(cost[order[i]]);
+        for (long long i = n - 1; i >= 0; i--) tail[i] = tail[i + 1] + chain[i];
+        // lanes a warp may keep busy if its longest chain c has to finish within T (units of t1)
+        auto cap_for = [&](double c, double T) {
+            const double x = (T / c - 1.0) / GAIN;
+            if (x >= 0.98) return 32;
+            if (x <= 0.0) return 1;
+            const int k = (int)(1.0 - KDEC * log(1.0 - x));
+            return k < 1 ? 1 : (k > 32 ? 32 : k);
+        };
+        // Pick the deadline T: the budgeted warps finish by T by construction; whatever is not
+        // handed out statically runs on the remaining warps at full width.  A small T isolates
+        // the long chains but leaves few full-width warps; scan T upwards from the longest chain
+        // and keep the T with the smallest predicted makespan max(T, queue time).
+        double best_T = chain[0], best_span = 1e300;
+        for (double T = chain[0] * 1.02; T < chain[0] * 40.0; T *= 1.04) {
+            long long pos = 0;
+            int used = 0;
+            while (used < nwarps && pos < n) {
+                const int k = cap_for(chain[pos], T);
+                if (k >= (int)lpw) break;
+                pos += k;
+                used++;
+            }
+            const int full = nwarps - used;
+            const double queue = full > 0 ? tail[pos] / (32.0 * full) * T32 : (pos < n ? 1e300 : 0.0);
+            const double span = T > queue ? T : queue;
+            if (span < best_span) { best_span = span; best_T = T; }
+            if (queue <= T) break;        // larger T only makes the deadline later
+        }
         long long pos = 0;
         for (int r = 0; r < nwarps; r++) {
             const int gw = border[r / warps_per_block] * warps_per_block + r % warps_per_block;
             if (pos >= n) continue;
-            const double ratio = exp(cmax - cost[order[pos]]);   // c_max / c (costs are logarithms)
-            const double x = ((1.0 + MARGIN) * ratio - 1.0) / GAIN;      // allowed slow-down / GAIN
-            const double k = x >= 0.98 ? 32.0 : 1.0 - KDEC * log(1.0 - x);
-            int cap = k >= (double)lpw ? (int)lpw : (int)k;
-            if (cap < 1) cap = 1;
+            int cap = cap_for(chain[pos], best_T);
+            if (cap > (int)lpw) cap = (int)lpw;
             wfirst[gw] = (int)pos;
             wcap[gw] = cap;
             pos += cap;
         }
         p->n_initial = (unsigned long long)(pos < n ? pos : n);
         p->probe_smid = smid;
+        if (getenv("SONIC_DEBUG"))
+            fprintf(stderr, "[sonic] schedule: longest chain %.3g ticks, deadline %.2f x, predicted makespan %.2f x\n",
+                    chain[0], best_T / chain[0], best_span / chain[0]);
     }
     TRYA(cudaMemcpyAsync(p->d_warp_first, wfirst.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     TRYA(cudaMemcpyAsync(p->d_warp_cap, wcap.data(), nwarps * sizeof(int), cudaMemcpyHostToDevice, p->stream));

@@ -153,7 +153,11 @@ def test_cost_sharding_round_robin():
     f = np.array([2e4, 5e5, 4e6, 2e4, 5e5, 4e6, 1e5, 1e6])
     A = np.array([6e5, 6e5, 6e5, 0., 1e3, 1e4, 3e5, 1e5])
     cost = predicted_log_cost(a, f, A)
-    assert np.argmax(cost) == 0           # 20 kHz / 600 kPa is the dearest point
+    assert f[np.argmax(cost)] == 2e4 and f[np.argmin(cost)] == 4e6    # cost falls with frequency
+    Q = np.array([-1e-3, 0., 0., -1e-3, 0., 0., 0., 0.])
+    costq = predicted_log_cost(a, f, A, Q)
+    assert np.all(costq <= cost + 1e-12)  # without charges: the envelope over all charges
+    assert costq[0] > costq[1] > costq[2]  # 600 kPa: 20 kHz dearer than 500 kHz dearer than 4 MHz
     parts = [shard_indices(cost, r, 3) for r in range(3)]
     assert sorted(np.concatenate(parts).tolist()) == list(range(8))
     order = np.argsort(-cost, kind='stable')

@@ -15,7 +15,14 @@ from pysonic_b200 import _lib  # noqa: E402
 
 tag = sys.argv[1] if len(sys.argv) > 1 else 'c2'
 wl = sys.argv[2] if len(sys.argv) > 2 else 'c2'
-w = bench.workload(wl)
+if wl in ('c1', 'c2'):
+    w = bench.workload(wl)
+else:
+    # any neuron name: the default 4-D grid of run_lookups.py restricted to a = 32 nm (BASELINE C4)
+    w = bench.workload('c2')
+    pn_ = ps.getPointNeuron(wl)
+    Qmin, Qmax = pn_.Qbounds
+    w.update(neuron=wl, a=np.array([32e-9]), Q=np.arange(Qmin, Qmax + 1e-5, 1e-5))
 pn = ps.getPointNeuron(w['neuron'])
 bls = [ps.NeuronalBilayerSonophore(float(a), pn).abi_params() for a in w['a']]
 ia, f, A, Q = bench.flatten(w)

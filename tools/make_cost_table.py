@@ -1,7 +1,7 @@
 # -*- coding: utf-8 -*-
 ''' Build the work-queue cost table from a measured run of the RS 4-D grid.
 
-        python tools/make_cost_table.py gpurun_out/diag_<tag>.npz
+        python tools/make_cost_table.py gpurun_out/diag_<tag>.npz [more diag files ...]
 
     Input: per-point right-hand-side counts of BASELINE config 2 (tools/gpu_diag.py on the GPU
     box).  Output: log(cost) on a coarse (radius, frequency, amplitude bin, |charge| bin) grid,
@@ -20,24 +20,45 @@ import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 
 A_EDGES_KPA = [0., 0.05, 0.3, 0.7, 1.5, 3., 5., 8., 12., 20., 35., 60., 100., 170., 280., 450., 1e9]
-Q_EDGES = [0., 10., 20., 30., 40., 50., 60., 70., 80., 88., 95., 101., 1e9]   # |Q| in nC/cm2
+Q_EDGES = [0., 10., 20., 30., 40., 50., 60., 70., 80., 88., 95., 101., 110., 125., 140., 160., 180., 200.,
+           225., 250., 275., 1e9]   # |Q| in nC/cm2
 
 
 def main():
-    d = np.load(sys.argv[1])
     a_nodes = np.array([16e-9, 32e-9, 64e-9])
-    f_nodes = np.unique(d['f'])
-    ia, f, A, Q, nr = d['ia'], d['f'], d['A'], d['Q'], d['nrhs'].astype(float)
-    jA = np.digitize(A * 1e-3, A_EDGES_KPA) - 1
-    jQ = np.digitize(np.abs(Q) * 1e5 + 1e-9, Q_EDGES) - 1
-    jf = np.searchsorted(f_nodes, f)
+    f_nodes = None
     nA, nQ = len(A_EDGES_KPA) - 1, len(Q_EDGES) - 1
-    tab = np.zeros((a_nodes.size, f_nodes.size, nA, nQ))
-    np.maximum.at(tab, (ia, jf, jA, jQ), nr)
-    assert (tab > 0).all(), 'empty bin'
-    tab = np.log(tab)
+    tab = None
+    parts = []
+    for path in sys.argv[1:]:
+        d = np.load(path)
+        if f_nodes is None:
+            f_nodes = np.unique(d['f'])
+            tab = np.zeros((a_nodes.size, f_nodes.size, nA, nQ))
+        # radius index of the file's own grid -> index in a_nodes (files of one radius hold 32 nm)
+        ia = d['ia'] if d['ia'].max() > 0 else np.full(d['ia'].shape, 1)
+        f, A, Q, nr = d['f'], d['A'], d['Q'], d['nrhs'].astype(float)
+        jA = np.digitize(A * 1e-3, A_EDGES_KPA) - 1
+        jQ = np.digitize(np.abs(Q) * 1e5 + 1e-9, Q_EDGES) - 1
+        jf = np.searchsorted(f_nodes, f)
+        np.maximum.at(tab, (ia, jf, jA, jQ), nr)
+        parts.append((ia, jf, jA, jQ, nr))
+    have = tab > 0
+    with np.errstate(divide='ignore'):
+        tab = np.log(tab)
+    # bins without data (large |Q| at 16 / 64 nm): the 32 nm value of the same (f, A, |Q|) bin shifted
+    # by the radius offset seen at the largest |Q| bin that has data for that radius
+    for i in (0, 2):
+        for j in range(f_nodes.size):
+            for k in range(nA):
+                lq = np.where(have[i, j, k])[0].max()
+                off = tab[i, j, k, lq] - tab[1, j, k, lq]
+                for l in range(nQ):
+                    if not have[i, j, k, l]:
+                        tab[i, j, k, l] = tab[1, j, k, l] + off
+    assert np.isfinite(tab).all(), 'empty bin'
     out = {'a': a_nodes.tolist(), 'f': f_nodes.tolist(), 'A_edges_kPa': A_EDGES_KPA, 'absQ_edges_nCcm2': Q_EDGES,
-           'log_cost': np.round(tab, 3).tolist(), 'source': os.path.basename(sys.argv[1])}
+           'log_cost': np.round(tab, 3).tolist(), 'source': [os.path.basename(x) for x in sys.argv[1:]]}
     with open(os.path.join(ROOT, 'pysonic_b200', 'data', 'cost_table.json'), 'w') as fh:
         json.dump(out, fh)
     with open(os.path.join(ROOT, 'pysonic_b200', 'csrc', 'generated', 'cost_table.h'), 'w') as fh:
@@ -56,9 +77,10 @@ def main():
             fh.write('    ' + ', '.join(f'{v:.3f}f' for v in flat[i:i + 12]) + ',\n')
         fh.write('};\n')
     # quality of the envelope on the source data
-    pred = tab[ia, jf, jA, jQ]
-    r = np.log(nr) - pred
-    print('table', tab.shape, 'mean over-prediction (log)', float(-r.mean()), 'max under-prediction', float(r.max()))
+    for path, (ia, jf, jA, jQ, nr) in zip(sys.argv[1:], parts):
+        r = np.log(nr) - tab[ia, jf, jA, jQ]
+        print(os.path.basename(path), 'mean over-prediction (log)', float(-r.mean()), 'max under-prediction', float(r.max()))
+    print('table', tab.shape)
 
 
 if __name__ == '__main__':
