@@ -24,6 +24,8 @@
  *                         point (nbls.py:153); used by multi-process sharding.
  *   sonic_plan_*       <- split form of sonic_points_run (upload / launch / fetch) so that a
  *                         caller can keep inputs resident on the device and time the kernels.
+ *   sonic_plan_fetch_relcm <- BilayerSonophore.getRelCmCycle (bls.py:806-808) for every point of the
+ *                         plan: what scripts/run_Cm_lookups.py:19-64 tabulates.
  *   sonic_mean_rates   <- PointNeuron.getEffRates(Vm) (pneuron.py:268-271).
  *   sonic_eval_rates   <- the neuron's alphax/betax/xinf/taux methods evaluated elementwise
  *                         (PySONIC/neurons/*.py), for testing the generated device functions.
@@ -136,6 +138,10 @@ int sonic_plan_fetch(SonicPlan* plan, double* out_tables, int32_t* out_ncycles,
                      uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs);
 /* Last-cycle deflection profiles Z[n][1000] (m) of the last launch (bls.py:806-813). */
 int sonic_plan_fetch_zprofiles(SonicPlan* plan, double* out_z);
+/* Relative capacitance profiles Cm(Z(t)) / Cm0 [n][1000] of the last cycle of the last launch:
+ * BilayerSonophore.getRelCmCycle (bls.py:806-808), the per-point output of
+ * scripts/run_Cm_lookups.py:19-64. */
+int sonic_plan_fetch_relcm(SonicPlan* plan, double* out_cm);
 int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
 int sonic_plan_destroy(SonicPlan* plan);
 

@@ -20,6 +20,7 @@
     `NEURONS` rate functions      `neurons/*.py`, helpers `pneuron.py:351-413`,
                                   alpha/beta from xinf/tau: `translators.py:317-324`
     `compute_astim_lookup`        `scripts/run_lookups.py:22-175`, `batches.py:135-171`
+    `rel_cm_cycle`, `compute_cm_lookup`  `bls.py:801-808`, `scripts/run_Cm_lookups.py:19-64`
     ============================  =====================================================
 
     The numerical integrator is the reference's own third-party dependency: scipy's ODEPACK
@@ -501,6 +502,21 @@ def compute_effvars(name, b, f, A, fs, Qm, stats=None, **kw):
     if stats is not None:
         stats['Z_cycle'] = Z_cycle
     return out, ncycles
+
+
+def rel_cm_cycle(b, f, A, Qm=0.):
+    ''' Relative capacitance profile over the last cycle (bls.py:801-808: getZlast,
+        getRelCmCycle), the per-point function of scripts/run_Cm_lookups.py:19-64. '''
+    tall, yall, ncycles = sim_cycles(b, f, A, Qm)
+    return v_capacitance(b, yall[-NPC_DENSE:, 1]) / b.Cm0
+
+
+def compute_cm_lookup(b, fref, Aref):
+    ''' Restatement of run_Cm_lookups.py:19-64. :return: (refs, tables) '''
+    fref, Aref = np.asarray(fref, float), np.asarray(Aref, float)
+    prof = np.array([rel_cm_cycle(b, f, A, 0.) for f in fref for A in Aref])
+    refs = {'f': fref, 'A': Aref, 't': np.linspace(0., 1., prof.shape[1])}
+    return refs, {'Cm_rel': prof.reshape(fref.size, Aref.size, -1)}
 
 
 def _point(args):

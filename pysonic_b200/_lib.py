@@ -60,6 +60,7 @@ EXPORTS = {
     'sonic_plan_sync': (C.c_int, [C.c_void_p]),
     'sonic_plan_fetch': (C.c_int, [C.c_void_p, _dp, _ip, _up, _dp, _up]),
     'sonic_plan_fetch_zprofiles': (C.c_int, [C.c_void_p, _dp]),
+    'sonic_plan_fetch_relcm': (C.c_int, [C.c_void_p, _dp]),
     'sonic_plan_stats': (C.c_int, [C.c_void_p, _sp]),
     'sonic_plan_destroy': (C.c_int, [C.c_void_p]),
     'sonic_trim': (C.c_int, []),
@@ -195,6 +196,12 @@ class Plan:
         z = np.empty((self.n, 1000))
         check(load().sonic_plan_fetch_zprofiles(self._h, _d(z)))
         return z
+
+    def fetch_relcm(self):
+        ''' Cm(Z(t)) / Cm0 over the last cycle, [n, 1000]. '''
+        cm = np.empty((self.n, 1000))
+        check(load().sonic_plan_fetch_relcm(self._h, _d(cm)))
+        return cm
 
     def stats(self):
         st = SonicStats()

@@ -62,6 +62,35 @@ class BilayerSonophore:
     def Zmin(self):
         return self.rel_Zmin * self.Delta
 
+    def _zprofiles(self, f, A, Qm, relcm, device=0):
+        ''' Last-cycle profiles for arrays of (f, A, Qm): Z (m) or Cm / Cm0, [n, 1000]. '''
+        from . import _lib
+        f, A, Qm = np.broadcast_arrays(np.asarray(f, float), np.asarray(A, float), np.asarray(Qm, float))
+        n = f.size
+        # the averaging stage of the plan needs a neuron; its tables are simply not fetched here
+        plan = _lib.Plan(device, [self.abi_params()], 0, 8, np.zeros(n, np.int32), f.ravel(), A.ravel(),
+                         Qm.ravel(), np.array([1.0]))
+        try:
+            plan.launch()
+            return plan.fetch_relcm() if relcm else plan.fetch_zprofiles()
+        finally:
+            plan.destroy()
+
+    def getZlast(self, drive, Qm):
+        ''' Deflection vector (m) of the last acoustic cycle (bls.py:801-803). '''
+        return self._zprofiles(drive.f, drive.A, Qm, relcm=False)[0]
+
+    def getRelCmCycle(self, drive, Qm):
+        ''' Relative capacitance vector of the last acoustic cycle (bls.py:806-808). '''
+        return self._zprofiles(drive.f, drive.A, Qm, relcm=True)[0]
+
+    @property
+    def Cm_lkp_filename(self):
+        return f'Cm_lkp_{self.a * 1e9:.0f}nm.pkl'        # bls.py:810-812
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.a * 1e9:.1f} nm)'
+
     def abi_params(self):
         ''' dict matching the SonicBlsParams struct of the C ABI. '''
         return {'a': self.a, 'Delta': self.Delta, 'Cm0': self.Cm0, 'depth': self.d, **self.LJ_approx}

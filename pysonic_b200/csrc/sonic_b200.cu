@@ -321,6 +321,18 @@ __global__ void __launch_bounds__(256) sonic_mean_rates_kernel(const double* __r
     }
 }
 
+// Relative capacitance profiles Cm(Z(t)) / Cm0 of the last cycle (bls.py:806-808).
+__global__ void __launch_bounds__(256) sonic_relcm_kernel(const double* __restrict__ zbuf, const int* __restrict__ ia,
+                                                          const SonicBls* __restrict__ radii, long long n,
+                                                          double* __restrict__ out) {
+    const long long total = n * SONIC_NPC;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (long long)gridDim.x * blockDim.x) {
+        const SonicBls b = radii[ia[k / SONIC_NPC]];
+        out[k] = sonic_capacitance(b.a * b.a, b.Delta, b.Cm0, zbuf[k]) / b.Cm0;
+    }
+}
+
 // FP64 FMA peak: 8 independent register chains per thread.
 __global__ void __launch_bounds__(256) sonic_dfma_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
@@ -849,6 +861,23 @@ int sonic_plan_fetch_zprofiles(SonicPlan* p, double* out_z) {
     CUDA_TRY(cudaMemcpyAsync(out_z, p->d_zbuf, (size_t)p->n * SONIC_NPC * sizeof(double),
                              cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SONIC_OK;
+}
+
+int sonic_plan_fetch_relcm(SonicPlan* p, double* out_cm) {
+    if (!p || !p->launched || !out_cm) return set_err(SONIC_E_ARG, "plan not launched or null buffer");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t total = (size_t)p->n * SONIC_NPC;
+    double* d_cm = nullptr;
+    CUDA_TRY(dalloc(&d_cm, total));
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    sonic_relcm_kernel<<<blocks, 256, 0, p->stream>>>(p->d_zbuf, p->d_ia, p->d_radii, p->n, d_cm);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_cm, d_cm, total * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_cm);
+    if (e != cudaSuccess) return set_err(SONIC_E_CUDA, "relative capacitance fetch failed: %s", cudaGetErrorString(e));
+    p->launches += 1;
     return SONIC_OK;
 }
 

@@ -250,6 +250,26 @@ def gen_c2sub(amp_scale=1.0, tag=''):
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
 
 
+def _cm_point(args):
+    a, f, A, Qm = args
+    from PySONIC.core import BilayerSonophore
+    bls = BilayerSonophore(a, 1e-2, 0.0)
+    return bls.getRelCmCycle(AcousticDrive(f, A), Qm)
+
+
+def gen_cm():
+    ''' Relative-capacitance profiles of scripts/run_Cm_lookups.py (BilayerSonophore(32 nm, 1e-2, 0),
+        getRelCmCycle(drive, 0.), bls.py:806-813) on a sub-grid of its default (f, A) grid. '''
+    f = np.array([100e3, 500e3, 4e6])
+    A = c2_amps()[[0, 30, 41, 50]]
+    jobs = [(32e-9, ff, AA, 0.) for ff in f for AA in A]
+    with mp.get_context('fork').Pool(min(mp.cpu_count(), len(jobs))) as pool:
+        out = pool.map(_cm_point, jobs)
+    np.savez_compressed(os.path.join(HERE, 'cm_lkp_32nm_sub.npz'), a=32e-9, f=f, A=A,
+                        t=np.linspace(0., 1., out[0].size), Cm_rel=np.array(out).reshape(f.size, A.size, -1))
+    print('cm_lkp_32nm_sub.npz:', len(jobs), 'profiles of', out[0].size, 'samples')
+
+
 def gen_noise():
     ''' The reference re-run with the drive amplitude changed by +-2 ulp: its own
         reproducibility floor on the C1 grid and the C2 subsample. '''
@@ -265,7 +285,7 @@ def gen_noise():
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
-            'c2sub': gen_c2sub, 'noise': gen_noise,
+            'c2sub': gen_c2sub, 'cm': gen_cm, 'noise': gen_noise,
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():

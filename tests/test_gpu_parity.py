@@ -381,3 +381,30 @@ def test_plan_relaunch_is_deterministic(gpu):
     for i in (0, 17, 63):
         Vm = Q[i] / so.v_capacitance(b, z[i]) * 1e3
         assert np.mean(Vm) == pytest.approx(out2[0][0, i, 0], rel=1e-12)
+
+
+def test_cm_lookup(gpu, tmp_path):
+    ''' computeCmLookup (scripts/run_Cm_lookups.py:19-64) against profiles
+        produced by the reference, sample by sample, and its on-disk format. '''
+    ps = _ps()
+    g = load_grid('cm_lkp_32nm_sub.npz')
+    bls = ps.BilayerSonophore(32e-9, 1e-2, 0.0)
+    lkp = ps.computeCmLookup(bls, g['f'], g['A'], loglevel=10)
+    assert list(lkp.refs) == ['f', 'A', 't'] and list(lkp.tables) == ['Cm_rel']
+    assert lkp['Cm_rel'].shape == (3, 4, 1000)
+    np.testing.assert_array_equal(lkp.refs['t'], g['t'])
+    dev = np.abs(lkp['Cm_rel'] - g['Cm_rel']) / g['Cm_rel']
+    assert dev.max() <= 2e-4 and dev.mean() <= 2e-5, (dev.max(), dev.mean())
+    # A = 0: the capacitance stays at its quasi-static value all along the cycle
+    assert np.ptp(lkp['Cm_rel'][:, 0], axis=-1).max() < 1e-6
+    # single-point methods of the reference class
+    prof = bls.getRelCmCycle(ps.AcousticDrive(float(g['f'][1]), float(g['A'][2])), 0.)
+    np.testing.assert_array_equal(prof, lkp['Cm_rel'][1, 2])
+    z = bls.getZlast(ps.AcousticDrive(float(g['f'][1]), float(g['A'][2])), 0.)
+    b = so.BlsConsts.from_table(32e-9, 1e-2, 0.0)
+    np.testing.assert_allclose(so.v_capacitance(b, z) / b.Cm0, prof, rtol=1e-12)
+    fpath = os.path.join(tmp_path, bls.Cm_lkp_filename)
+    lkp.toPickle(fpath)
+    with open(fpath, 'rb') as fh:
+        d = pickle.load(fh)
+    assert list(d['refs']) == ['f', 'A', 't'] and d['tables']['Cm_rel'].shape == (3, 4, 1000)

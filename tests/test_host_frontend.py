@@ -162,3 +162,19 @@ def test_cost_sharding_round_robin():
     assert sorted(np.concatenate(parts).tolist()) == list(range(8))
     order = np.argsort(-cost, kind='stable')
     assert [p[0] for p in parts] == order[:3].tolist()
+
+
+def test_cm_lookup_validation_and_names():
+    ''' run_Cm_lookups.py:19-41 (same exception types) and bls.py:810-812 (file name). '''
+    bls = ps.BilayerSonophore(32e-9, 1e-2, 0.0)
+    assert bls.Cm_lkp_filename == 'Cm_lkp_32nm.pkl'
+    with pytest.raises(TypeError):
+        ps.computeCmLookup(bls, 500e3, np.array([0., 1e5]))
+    with pytest.raises(TypeError):
+        ps.computeCmLookup(bls, np.array([500e3]), np.array([0, 100000]))
+    with pytest.raises(ValueError):
+        ps.computeCmLookup(bls, np.array([]), np.array([0., 1e5]))
+    with pytest.raises(ValueError):
+        ps.computeCmLookup(bls, np.array([-1.]), np.array([0., 1e5]))
+    with pytest.raises(ValueError):
+        ps.computeCmLookup(bls, np.array([5e5]), np.array([-1.]))

@@ -182,3 +182,15 @@ def test_c1_grid_parity_statistics(hostsim):
     assert np.mean(same[stable]) >= 0.97
     hiA = np.repeat(g['A'][iA] >= 1e4, g['Q'].size)
     assert np.mean(same[hiA]) >= 0.99
+
+
+def test_capacitance_profiles_pointwise(hostsim):
+    ''' The whole last-cycle profile (what run_Cm_lookups.py tabulates), sample by sample. '''
+    g = load_grid('cm_lkp_32nm_sub.npz')
+    b = so.BlsConsts.from_table(32e-9, 1e-2, 0.0)
+    for i, f in enumerate(g['f']):
+        for j, A in enumerate(g['A']):
+            h = hostsim.point(b, float(f), float(A), 0.0)
+            cm = so.v_capacitance(b, h['z']) / b.Cm0
+            dev = np.abs(cm - g['Cm_rel'][i, j]) / g['Cm_rel'][i, j]
+            assert dev.max() <= 2e-4 and dev.mean() <= 2e-5, (f, A, dev.max(), dev.mean())

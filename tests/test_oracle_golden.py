@@ -74,3 +74,17 @@ def test_lookup_grid_layout_and_values():
         assert tables[k].shape == (1, 1, 3, 3, 1)
         np.testing.assert_allclose(tables[k], ref, rtol=TOL, atol=0)
     np.testing.assert_array_equal(ncyc, g['ncycles'][:, :, iA][:, :, :, iQ])
+
+
+def test_relative_capacitance_profiles():
+    ''' rel_cm_cycle (bls.py:801-808) against profiles produced by the reference's
+        BilayerSonophore(32 nm, 1e-2, 0).getRelCmCycle, the per-point function of run_Cm_lookups.py. '''
+    g = load_grid('cm_lkp_32nm_sub.npz')
+    b = so.BlsConsts.from_table(32e-9, 1e-2, 0.0)
+    for i in (1, 2):                      # 500 kHz and 4 MHz (the 100 kHz profiles take seconds each)
+        for j in range(g['A'].size):
+            prof = so.rel_cm_cycle(b, float(g['f'][i]), float(g['A'][j]), 0.)
+            np.testing.assert_allclose(prof, g['Cm_rel'][i, j], rtol=TOL, atol=0)
+    refs, tables = so.compute_cm_lookup(b, g['f'][2:], g['A'][:2])
+    assert list(refs) == ['f', 'A', 't'] and tables['Cm_rel'].shape == (1, 2, 1000)
+    np.testing.assert_array_equal(refs['t'], g['t'])
