@@ -232,15 +232,49 @@ SONIC_HD double sonic_mkdouble(int hi, int lo) {
 #endif
 }
 
+// Polynomial coefficients of the elementary functions below.  On the device they live in constant
+// memory, so that an FMA reads them as a constant-bank operand instead of materialising every
+// 64-bit literal with two moves (about 80 instructions per right-hand side otherwise).
+#if defined(__CUDACC__)
+#define SONIC_COEF_TABLE __device__ __constant__
+#else
+#define SONIC_COEF_TABLE static const
+#endif
+#define SONIC_COEF_VALUES                                                                          \
+    {                                                                                              \
+        /* 0..6: log, Lg1..Lg7 */                                                                  \
+        6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,              \
+        2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,              \
+        1.479819860511658591e-01,                                                                  \
+        /* 7..8: ln2_hi, ln2_lo;  9: log2(e) */                                                    \
+        6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634074,             \
+        /* 10..20: exp, 1/3! .. 1/13! */                                                           \
+        1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,              \
+        1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0,  \
+        /* 21..31: sin, -1/3!, 1/5!, ..., -1/23! */                                                \
+        -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0,                 \
+        1.0 / 6227020800.0, -1.0 / 1307674368000.0, 1.0 / 355687428096000.0,                       \
+        -1.0 / 121645100408832000.0, 1.0 / 51090942171709440000.0,                                 \
+        -1.0 / 25852016738884976640000.0,                                                          \
+        /* 32: 2 pi */                                                                             \
+        6.283185307179586477                                                                       \
+    }
+SONIC_COEF_TABLE double SONIC_K[33] = SONIC_COEF_VALUES;
+#if defined(__CUDACC__) && !defined(__CUDA_ARCH__)
+// host pass of nvcc: the host versions of the functions read a plain copy
+static const double SONIC_K_HOST[33] = SONIC_COEF_VALUES;
+#define SONIC_KC(i) SONIC_K_HOST[i]
+#else
+#define SONIC_KC(i) SONIC_K[i]
+#endif
+
 // Natural logarithm of a positive, finite, normal number.  Argument reduction and the
 // polynomial are the classical ones (x = 2^k m, m in [sqrt(1/2), sqrt(2)), s = f / (2 + f) with
 // f = m - 1, log(1 + f) = f - f^2/2 + s (f^2/2 + R(s^2)), R a degree-7 minimax polynomial).
 SONIC_HD double sonic_log(double x) {
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
+    const double ln2_hi = SONIC_KC(7), ln2_lo = SONIC_KC(8);
+    const double Lg1 = SONIC_KC(0), Lg2 = SONIC_KC(1), Lg3 = SONIC_KC(2), Lg4 = SONIC_KC(3),
+                 Lg5 = SONIC_KC(4), Lg6 = SONIC_KC(5), Lg7 = SONIC_KC(6);
     int hx = sonic_hiword(x);
     const int lx = sonic_loword(x);
     int k = (hx >> 20) - 1023;
@@ -263,19 +297,18 @@ SONIC_HD double sonic_log(double x) {
 // Exponential for |x| < 700: x = k ln2 + r, |r| <= ln2 / 2, degree-13 Taylor polynomial of
 // exp(r) (truncation 4e-18) in Estrin form, scaled by 2^k through the exponent field.
 SONIC_HD double sonic_exp(double x) {
-    const double L2E = 1.4426950408889634074, ln2_hi = 6.93147180369123816490e-01,
-                 ln2_lo = 1.90821492927058770002e-10;
+    const double L2E = SONIC_KC(9), ln2_hi = SONIC_KC(7), ln2_lo = SONIC_KC(8);
     const double kf = rint(x * L2E);
     double r = fma(-kf, ln2_hi, x);
     r = fma(-kf, ln2_lo, r);
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
     const double p01 = 1.0 + r;
-    const double p23 = fma(r, 1.0 / 6.0, 0.5);
-    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-    const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
-    const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
-    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double p23 = fma(r, SONIC_KC(10), 0.5);
+    const double p45 = fma(r, SONIC_KC(12), SONIC_KC(11));
+    const double p67 = fma(r, SONIC_KC(14), SONIC_KC(13));
+    const double p89 = fma(r, SONIC_KC(16), SONIC_KC(15));
+    const double pab = fma(r, SONIC_KC(18), SONIC_KC(17));
+    const double pcd = fma(r, SONIC_KC(20), SONIC_KC(19));
     const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
     const double s0 = fma(r4, q1, q0), s1 = fma(r4, pcd, q2);
     const double e = fma(r8, s1, s0);
@@ -288,15 +321,15 @@ SONIC_HD double sonic_sin_drive(double u) {
     double r = u - rint(u);
     const double rf = copysign(0.5, r) - r;
     r = (fabs(r) > 0.25) ? rf : r;
-    const double th = r * 6.283185307179586477;
+    const double th = r * SONIC_KC(32);
     const double z = th * th, z2 = z * z, z4 = z2 * z2;
     // 1 - z/3! + z^2/5! - ... - z^11/23!
-    const double c01 = fma(z, -1.0 / 6.0, 1.0);
-    const double c23 = fma(z, -1.0 / 5040.0, 1.0 / 120.0);
-    const double c45 = fma(z, -1.0 / 39916800.0, 1.0 / 362880.0);
-    const double c67 = fma(z, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
-    const double c89 = fma(z, -1.0 / 121645100408832000.0, 1.0 / 355687428096000.0);
-    const double cab = fma(z, -1.0 / 25852016738884976640000.0, 1.0 / 51090942171709440000.0);
+    const double c01 = fma(z, SONIC_KC(21), 1.0);
+    const double c23 = fma(z, SONIC_KC(23), SONIC_KC(22));
+    const double c45 = fma(z, SONIC_KC(25), SONIC_KC(24));
+    const double c67 = fma(z, SONIC_KC(27), SONIC_KC(26));
+    const double c89 = fma(z, SONIC_KC(29), SONIC_KC(28));
+    const double cab = fma(z, SONIC_KC(31), SONIC_KC(30));
     const double d0 = fma(z2, c23, c01), d1 = fma(z2, c67, c45), d2 = fma(z2, cab, c89);
     const double e0 = fma(z4, d1, d0);
     const double poly = fma(z4 * z4, d2, e0);
@@ -560,12 +593,14 @@ struct SonicLane {
 #endif
 };
 
+// max of two numbers as one compare and one select (fmax adds NaN bookkeeping; a NaN operand on
+// the right is dropped here exactly as fmax drops it)
+SONIC_HD double sonic_max(double a, double b) { return b > a ? b : a; }
+
 SONIC_HD double sonic_mnorm3(double v0, double v1, double v2, const double w[3]) {
-    double vm = 0.0;
-    vm = fmax(vm, fabs(v0) * w[0]);
-    vm = fmax(vm, fabs(v1) * w[1]);
-    vm = fmax(vm, fabs(v2) * w[2]);
-    return vm;
+    // weighted max-norm (LSODA's vmnorm); the three products are non-negative
+    const double p0 = fabs(v0) * w[0], p1 = fabs(v1) * w[1], p2 = fabs(v2) * w[2];
+    return sonic_max(sonic_max(p0, p1), p2);
 }
 
 SONIC_HD double sonic_mnorm(const double v[3], const double w[3]) {
