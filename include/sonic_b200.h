@@ -114,6 +114,17 @@ int sonic_points_run(int device, const SonicBlsParams* radii, int na, int neuron
                      uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs,
                      SonicStats* stats);
 
+/* Same with charge overtones (NeuronalBilayerSonophore.computeEffVars(..., Qm_overtones),
+ * nbls.py:169-201; grid construction run_lookups.py:105-128): the imposed charge of point i is the
+ * Fourier-series cycle Q0 + 2 sum_k A_k cos(2 pi j k / 1000 + phi_k), applied sample-and-hold
+ * (bls.py:766-768), with overtones[i][k] = {A_k (C/m2), phi_k (rad)}, k < novertones <= 4.
+ *   out_tables : [1 + 2 novertones + nrates][n][nfs]  ('V', then A_V1, phi_V1, ..., then rates) */
+int sonic_points_run_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                        const int32_t* ia, const double* f, const double* A, const double* Q,
+                        int novertones, const double* overtones, const double* fs, int nfs,
+                        double* out_tables, int32_t* out_ncycles, uint32_t* out_status,
+                        double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats);
+
 /* Full grid, reference queue order a > f > A > Q (> fs): out_tables is
  * [1 + nrates][na][nf][nA][nQ][nfs], the per-point outputs are [na][nf][nA][nQ].
  * device_mask: bit d set = use device d (0 = device 0 only). */
@@ -132,6 +143,10 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
  * the plan's private one, so that the caller can order and time the launches with its own
  * events.  The stream must belong to the plan's device and outlive the plan. */
 int sonic_plan_set_stream(SonicPlan* plan, void* stream);
+int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                         const int32_t* ia, const double* f, const double* A, const double* Q,
+                         int novertones, const double* overtones, const double* fs, int nfs,
+                         SonicPlan** plan);
 int sonic_plan_launch(SonicPlan* plan);   /* asynchronous on the plan's stream */
 int sonic_plan_sync(SonicPlan* plan);
 int sonic_plan_fetch(SonicPlan* plan, double* out_tables, int32_t* out_ncycles,

@@ -205,14 +205,19 @@ def sim_cycles(b, f, A, Qm, nmax=NCYCLES_MAX, nmin=2, stats=None, rtol=None, ato
     b.kA_tissue = 2 * (alpha_tissue * f) * b.d           # bls.py:583-586
     T = 1. / f
     dt = 1 / (NPC_DENSE * f)
-    Z0 = balancedef_qs(b, b.ng0, Qm, pac(f, A, dt))       # bls.py:720-725
-    yall = np.array([[0., 0.], [0., Z0], [b.ng0, b.ng0]]).T   # solvers.py:111-115
     tall = np.ones(2) * 0.
     nfe = [0]
 
+    if isinstance(Qm, float):
+        Qm0, Qm_t = Qm, lambda t: Qm                                  # bls.py:763-765
+    else:
+        Qm0, Qm_t = Qm[0], lambda t: Qm[int((t % T) / dt)]            # bls.py:766-768
+    Z0 = balancedef_qs(b, b.ng0, Qm0, pac(f, A, dt))      # bls.py:720-725,771-772
+    yall = np.array([[0., 0.], [0., Z0], [b.ng0, b.ng0]]).T   # solvers.py:111-115
+
     def dfunc(t, y):
         nfe[0] += 1
-        return derivatives(t, y, b, f, A, Qm)
+        return derivatives(t, y, b, f, A, Qm_t(t))
 
     kw = {}
     if rtol is not None:
@@ -487,16 +492,31 @@ def get_bls(name, a):
     return BlsConsts.from_table(a, Cm0, neuron_Qm0(name))
 
 
-def compute_effvars(name, b, f, A, fs, Qm, stats=None, **kw):
-    ''' :return: ([{V, rates...} per fs], ncycles) '''
+def compute_effvars(name, b, f, A, fs, Qm, stats=None, Qm_overtones=None, **kw):
+    ''' nbls.py:153-222.  Qm_overtones: list of (amplitude, phase) pairs or None.
+        :return: ([{V, [A_V1, phi_V1, ...], rates...} per fs], ncycles) '''
     fs = np.atleast_1d(np.asarray(fs, dtype=float))
-    tall, yall, ncycles = sim_cycles(b, f, A, Qm, stats=stats, **kw)
+    if Qm_overtones is None:
+        Qm_cycle = Qm                                     # nbls.py:169-172
+        novertones = 0
+    else:
+        A_Qm, phi_Qm = list(zip(*Qm_overtones))           # nbls.py:173-178
+        Qm_fft = np.hstack(([Qm + 0j], A_Qm * (np.cos(phi_Qm) + 1j * np.sin(phi_Qm))))
+        Qm_cycle = np.fft.irfft(Qm_fft, n=NPC_DENSE) * NPC_DENSE
+        novertones = len(A_Qm)
+    tall, yall, ncycles = sim_cycles(b, f, A, Qm_cycle, stats=stats, **kw)
     Z_cycle = yall[-NPC_DENSE:, 1]                    # nbls.py:181
     Cm_cycle = v_capacitance(b, Z_cycle)              # nbls.py:182
     out = []
     for x in fs:
-        Vm_cycle = Qm / (x * Cm_cycle + (1 - x) * b.Cm0) * 1e3   # nbls.py:148-151,188
+        Vm_cycle = Qm_cycle / (x * Cm_cycle + (1 - x) * b.Cm0) * 1e3   # nbls.py:148-151,188
         ev = {'V': np.mean(Vm_cycle)}
+        if novertones > 0:                                # nbls.py:194-201
+            Vm_coeffs = np.fft.rfft(Vm_cycle)[:novertones + 1] / NPC_DENSE
+            A_Vm, phi_Vm = np.abs(Vm_coeffs), np.angle(Vm_coeffs)
+            for i in range(1, novertones + 1):
+                ev[f'A_V{i}'] = A_Vm[i]
+                ev[f'phi_V{i}'] = phi_Vm[i]
         ev.update(eff_rates(name, Vm_cycle))
         out.append(ev)
     if stats is not None:

@@ -51,10 +51,14 @@ EXPORTS = {
     'sonic_mean_rates': (C.c_int, [C.c_int, C.c_int, _dp, C.c_int64, _dp]),
     'sonic_points_run': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, _dp,
                                    C.c_int, _dp, _ip, _up, _dp, _up, _sp]),
+    'sonic_points_run_ex': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, C.c_int, _dp,
+                                      _dp, C.c_int, _dp, _ip, _up, _dp, _up, _sp]),
     'sonic_lookup_run': (C.c_int, [_bp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int,
                                    C.c_int, C.c_uint32, _dp, _ip, _up, _dp, _sp]),
     'sonic_plan_create': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, _dp,
                                     C.c_int, C.POINTER(C.c_void_p)]),
+    'sonic_plan_create_ex': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, C.c_int, _dp,
+                                       _dp, C.c_int, C.POINTER(C.c_void_p)]),
     'sonic_plan_set_stream': (C.c_int, [C.c_void_p, C.c_void_p]),
     'sonic_plan_launch': (C.c_int, [C.c_void_p]),
     'sonic_plan_sync': (C.c_int, [C.c_void_p]),
@@ -161,16 +165,18 @@ def fp64_peak(device=0):
 class Plan:
     ''' Device-resident batch of (radius, f, A, Q) points (split form of sonic_points_run). '''
 
-    def __init__(self, device, bls_params, neuron_id, nrates, ia, f, A, Q, fs):
+    def __init__(self, device, bls_params, neuron_id, nrates, ia, f, A, Q, fs, overtones=None):
         lib = load()
         self.ia = np.ascontiguousarray(ia, dtype=np.int32)
         self.f, self.A, self.Q, self.fs = as_f64(f), as_f64(A), as_f64(Q), as_f64(fs)
-        self.n, self.nfs, self.nvar = self.f.size, self.fs.size, 1 + nrates
+        self.ov, nov = as_overtones(overtones, self.f.size)
+        self.n, self.nfs, self.nvar = self.f.size, self.fs.size, 1 + 2 * nov + nrates
         self._bls = bls_array(bls_params)
         self._h = C.c_void_p()
-        check(lib.sonic_plan_create(device, self._bls, len(bls_params), neuron_id, self.n,
-                                    self.ia.ctypes.data_as(_ip), _d(self.f), _d(self.A), _d(self.Q),
-                                    _d(self.fs), self.nfs, C.byref(self._h)))
+        check(lib.sonic_plan_create_ex(device, self._bls, len(bls_params), neuron_id, self.n,
+                                       self.ia.ctypes.data_as(_ip), _d(self.f), _d(self.A), _d(self.Q),
+                                       nov, _d(self.ov) if nov else None, _d(self.fs), self.nfs,
+                                       C.byref(self._h)))
 
     def set_stream(self, cuda_stream):
         ''' Launch on a caller-owned stream (integer cudaStream_t handle). '''
@@ -220,24 +226,35 @@ class Plan:
             pass
 
 
-def points_run(device, bls_params, neuron_id, nrates, ia, f, A, Q, fs):
-    ''' One-shot call of sonic_points_run with host buffers.
-        :return: (tables[1+nrates, n, nfs], ncycles[n], status[n], tpoint[n], nrhs[n], stats) '''
+def as_overtones(overtones, n):
+    ''' None or array-like [n, nov, 2] of (amplitude C/m2, phase rad) -> (contiguous array, nov) '''
+    if overtones is None:
+        return None, 0
+    ov = np.ascontiguousarray(np.asarray(overtones, dtype=np.float64))
+    if ov.ndim != 3 or ov.shape[0] != n or ov.shape[2] != 2:
+        raise ValueError(f'charge overtones must have shape (n, novertones, 2), got {ov.shape}')
+    return ov, ov.shape[1]
+
+
+def points_run(device, bls_params, neuron_id, nrates, ia, f, A, Q, fs, overtones=None):
+    ''' One-shot call of sonic_points_run(_ex) with host buffers.
+        :return: (tables[1+2*nov+nrates, n, nfs], ncycles[n], status[n], tpoint[n], nrhs[n], stats) '''
     lib = load()
     ia = np.ascontiguousarray(ia, dtype=np.int32)
     f, A, Q, fs = as_f64(f), as_f64(A), as_f64(Q), as_f64(fs)
     n, nfs = f.size, fs.size
-    out = np.empty((1 + nrates, n, nfs))
+    ov, nov = as_overtones(overtones, n)
+    out = np.empty((1 + 2 * nov + nrates, n, nfs))
     ncyc = np.empty(n, dtype=np.int32)
     status = np.empty(n, dtype=np.uint32)
     tpoint = np.empty(n)
     nrhs = np.empty(n, dtype=np.uint32)
     st = SonicStats()
     arr = bls_array(bls_params)
-    check(lib.sonic_points_run(device, arr, len(bls_params), neuron_id, n, ia.ctypes.data_as(_ip),
-                               _d(f), _d(A), _d(Q), _d(fs), nfs, _d(out), ncyc.ctypes.data_as(_ip),
-                               status.ctypes.data_as(_up), _d(tpoint), nrhs.ctypes.data_as(_up),
-                               C.byref(st)))
+    check(lib.sonic_points_run_ex(device, arr, len(bls_params), neuron_id, n, ia.ctypes.data_as(_ip),
+                                  _d(f), _d(A), _d(Q), nov, _d(ov) if nov else None, _d(fs), nfs, _d(out),
+                                  ncyc.ctypes.data_as(_ip), status.ctypes.data_as(_up), _d(tpoint),
+                                  nrhs.ctypes.data_as(_up), C.byref(st)))
     return out, ncyc, status, tpoint, nrhs, st.asdict()
 
 

@@ -43,8 +43,7 @@ class Batch:
         ''' Run the batch; outputs are returned in queue order. '''
         t0 = time.perf_counter()
         nbls = self._effvars_owner()
-        if nbls is not None and len(self.queue) > 0 and all(
-                isinstance(q, list) and len(q) == 3 for q in self.queue):
+        if nbls is not None and len(self.queue) > 0 and self._is_effvars_queue():
             outputs = self._run_effvars(nbls)
         else:
             outputs = []
@@ -54,18 +53,47 @@ class Batch:
         logger.info('Batch of %d job(s) completed in %.3f s', len(self.queue), time.perf_counter() - t0)
         return outputs
 
+    def _items(self):
+        ''' Queue items as (drive, fs, Qm, overtones or None): either [drive, fs, Qm] lists or
+            ([drive, fs, Qm], {'Qm_overtones': [...]}) tuples (run_lookups.py:100-128), or
+            [drive, fs, Qm, overtones] lists (tests/test_Qovertones.py:48-51). '''
+        out = []
+        for q in self.queue:
+            args, kwargs = self.resolve(q)
+            ov = kwargs.get('Qm_overtones') if kwargs else None
+            if len(args) == 4:
+                ov = args[3]
+            out.append((args[0], args[1], args[2], ov))
+        return out
+
+    def _is_effvars_queue(self):
+        try:
+            for q in self.queue:
+                args, kwargs = self.resolve(q)
+                if len(args) not in (3, 4) or not (hasattr(args[0], 'f') and hasattr(args[0], 'A')):
+                    return False
+                if kwargs and set(kwargs) - {'Qm_overtones'}:
+                    return False
+        except TypeError:
+            return False
+        return True
+
     def _run_effvars(self, nbls):
-        ''' One GPU launch for the whole queue.  Items are [drive, fs, Qm]; all items must share
-            the same fs vector to be batched together (run_lookups.py:100-103 builds them so). '''
-        fs0 = np.atleast_1d(np.asarray(self.queue[0][1], float))
-        same_fs = all(np.array_equal(np.atleast_1d(np.asarray(q[1], float)), fs0) for q in self.queue)
-        if not same_fs:
-            return [nbls.computeEffVars(*q) for q in self.queue]
-        f = np.array([q[0].f for q in self.queue])
-        A = np.array([q[0].A for q in self.queue])
-        Q = np.array([float(q[2]) for q in self.queue])
-        out, ncyc, status, tpoint, _, _ = nbls.effvars_batch(f, A, Q, fs0)
-        keys = ['V'] + nbls.pneuron.rates
+        ''' One GPU launch for the whole queue.  All items must share the same fs vector and
+            number of charge overtones to be batched together (run_lookups.py builds them so). '''
+        items = self._items()
+        fs0 = np.atleast_1d(np.asarray(items[0][1], float))
+        nov0 = 0 if items[0][3] is None else len(items[0][3])
+        uniform = all(np.array_equal(np.atleast_1d(np.asarray(q[1], float)), fs0) and
+                      (0 if q[3] is None else len(q[3])) == nov0 for q in items)
+        if not uniform:
+            return [nbls.computeEffVars(q[0], q[1], q[2], q[3]) for q in items]
+        f = np.array([q[0].f for q in items])
+        A = np.array([q[0].A for q in items])
+        Q = np.array([float(q[2]) for q in items])
+        ov = np.array([np.asarray(q[3], float).reshape(-1, 2) for q in items]) if nov0 else None
+        out, ncyc, status, tpoint, _, _ = nbls.effvars_batch(f, A, Q, fs0, overtones=ov)
+        keys = nbls.effvars_keys(nov0)
         res = []
         for n in range(len(self.queue)):
             effvars = [{k: out[i, n, j] for i, k in enumerate(keys)} for j in range(fs0.size)]

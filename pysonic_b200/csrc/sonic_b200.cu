@@ -76,6 +76,8 @@ struct SonicJob {
     const double* f;
     const double* A;
     const double* Q;
+    const double* ov;          // [n][nov][2] charge overtones (amplitude, phase), or null
+    int nov;
     double* z0;
     double* zbuf;              // [n][1000]
     double* ngbuf;             // [slots][1000]
@@ -106,7 +108,9 @@ __global__ void __launch_bounds__(128) sonic_z0_kernel(SonicJob job) {
     if (i >= job.n) return;
     SonicPoint p;
     const double f = job.f[i];
-    sonic_point_init(p, job.radii[job.ia[i]], f, job.A[i], job.Q[i]);
+    sonic_point_init(p, job.radii[job.ia[i]], f, job.A[i], job.Q[i], job.nov,
+                     job.nov ? job.ov + (size_t)i * 2 * job.nov : nullptr);
+    if (p.nov) sonic_update_charge(p, 0.0);       // initial conditions use the first charge sample (bls.py:766)
     double z0;
     const bool ok = sonic_z0(p, f, &z0);
     job.z0[i] = ok ? z0 : nan("");
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
             if (q < (unsigned long long)job.n) {
                 pt = job.order[q];
                 const double f = job.f[pt];
-                sonic_point_init(p, job.radii[job.ia[pt]], f, job.A[pt], job.Q[pt]);
+                sonic_point_init(p, job.radii[job.ia[pt]], f, job.A[pt], job.Q[pt], job.nov,
+                                 job.nov ? job.ov + (size_t)pt * 2 * job.nov : nullptr);
                 period = 1.0 / f;
                 sink.zbuf = job.zbuf + pt * SONIC_NPC;
                 const double z0 = job.z0[pt];
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
         }
         if (active) {
             double fv[3];
+            if (p.nov) sonic_update_charge(p, s.tn);
             if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
             sonic_tick(s, H, &tab, p, sink, period, fv, wmask);
             if (s.phase == PH_DONE) {
@@ -230,15 +236,19 @@ __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS)
 sonic_average_kernel(const double* __restrict__ zbuf, const int* __restrict__ ia,
                      const double* __restrict__ Q, const SonicBls* __restrict__ radii,
                      const unsigned* __restrict__ status, long long n,
-                     const double* __restrict__ fs, int nfs, double* __restrict__ out) {
+                     const double* __restrict__ fs, int nfs, int nov, const double* __restrict__ ov,
+                     double* __restrict__ out) {
     constexpr int NR = SonicRates<NID>::N;
+    constexpr int NV = 1 + 2 * SONIC_MAX_OVERTONES + NR;
     __shared__ double cm_s[SONIC_AVG_WARPS][SONIC_NPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * SONIC_AVG_WARPS;
+    const int nvar = 1 + 2 * nov + NR;          // V, (A_Vk, phi_Vk) per overtone, rates
     for (long long pt = (long long)blockIdx.x * SONIC_AVG_WARPS + warp; pt < n; pt += nwarps) {
         const SonicBls b = radii[ia[pt]];
         const double a2 = b.a * b.a;
-        const double q = Q[pt];
+        const double q0 = Q[pt];
+        const double* ovp = nov ? ov + (size_t)pt * 2 * nov : nullptr;
         const bool bad = (status[pt] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
                                         SONIC_ST_TOLSF)) != 0;
         const double* z = zbuf + pt * SONIC_NPC;
@@ -247,32 +257,49 @@ sonic_average_kernel(const double* __restrict__ zbuf, const int* __restrict__ ia
         __syncwarp();
         for (int j = 0; j < nfs; j++) {
             const double x = fs[j];
-            double acc[1 + NR];
+            double acc[NV];
 #pragma unroll
-            for (int v = 0; v <= NR; v++) acc[v] = 0.0;
+            for (int v = 0; v < NV; v++) acc[v] = 0.0;
             for (int k = lane; k < SONIC_NPC; k += 32) {
+                // imposed charge of sample k (constant without overtones, nbls.py:169-178)
+                const double q = nov ? sonic_charge_sample(q0, nov, ovp, k) : q0;
                 // spatial average of the capacitance, then membrane potential in mV
                 const double vm = q / (x * cm[k] + (1 - x) * b.Cm0) * 1e3;   // nbls.py:148-151,188
                 double r[NR];
                 SonicRates<NID>::eval(vm, r);
                 acc[0] += vm;
+                // Fourier coefficients of the potential, rfft(Vm)[m] (nbls.py:194-201)
+                for (int m = 1; m <= nov; m++) {
+                    double sn, cs;
+                    sincospi((double)((2 * m * k) % (2 * SONIC_NPC)) * (1.0 / SONIC_NPC), &sn, &cs);
+                    acc[2 * m - 1] += vm * cs;
+                    acc[2 * m] -= vm * sn;
+                }
 #pragma unroll
-                for (int v = 0; v < NR; v++) acc[1 + v] += r[v];
+                for (int v = 0; v < NR; v++) acc[1 + 2 * SONIC_MAX_OVERTONES + v] += r[v];
             }
 #pragma unroll
-            for (int v = 0; v <= NR; v++) {
+            for (int v = 0; v < NV; v++) {
                 double t = acc[v];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                acc[v] = t;
+                acc[v] = t * (1.0 / (double)SONIC_NPC);
             }
-            // lane v stores table v (mean over the 1000 samples of the cycle)
+            // amplitude-phase form of the overtone coefficients
+            for (int m = 1; m <= nov; m++) {
+                const double re = acc[2 * m - 1], im = acc[2 * m];
+                acc[2 * m - 1] = hypot(re, im);
+                acc[2 * m] = atan2(im, re);
+            }
+            // lane v stores table v
             double mine = 0.0;
 #pragma unroll
-            for (int v = 0; v <= NR; v++)
-                if (lane == v) mine = acc[v];
-            if (lane <= NR)
-                out[((long long)lane * n + pt) * nfs + j] = bad ? nan("") : mine / (double)SONIC_NPC;
+            for (int v = 0; v < NV; v++) {
+                const int tv = v <= 2 * nov ? v : v - 2 * SONIC_MAX_OVERTONES + 2 * nov;   // table of slot v
+                const bool used = v <= 2 * nov || v > 2 * SONIC_MAX_OVERTONES;
+                if (used && lane == tv) mine = acc[v];
+            }
+            if (lane < nvar) out[((long long)lane * n + pt) * nfs + j] = bad ? nan("") : mine;
         }
         __syncwarp();
     }
@@ -432,6 +459,9 @@ struct SonicPlan {
     int neuron_id = 0;
     int nrates = 0;
     int na = 0, nfs = 0;
+    int nov = 0;               // charge overtones per point
+    int nvar = 0;              // tables per point: 1 + 2 nov + nrates
+    double* d_ov = nullptr;
     long long n = 0;
     long long slots = 0;
     int grid = 0, lanes_per_warp = 32;
@@ -465,7 +495,7 @@ static int plan_free(SonicPlan* p) {
     cudaFree(p->d_radii); cudaFree(p->d_order); cudaFree(p->d_ia); cudaFree(p->d_ncycles);
     cudaFree(p->d_f); cudaFree(p->d_A); cudaFree(p->d_Q); cudaFree(p->d_fs); cudaFree(p->d_z0);
     pool_give(p->device, 0, p->d_zbuf, p->zbuf_count); pool_give(p->device, 1, p->d_ngbuf, p->ngbuf_count);
-    cudaFree(p->d_tpoint); cudaFree(p->d_out);
+    cudaFree(p->d_tpoint); cudaFree(p->d_out); cudaFree(p->d_ov);
     cudaFree(p->d_status); cudaFree(p->d_nfe); cudaFree(p->d_nje); cudaFree(p->d_nsteps);
     cudaFree(p->d_counter); cudaFree(p->d_warp_first); cudaFree(p->d_warp_cap); cudaFree(p->d_block_smid);
     for (auto& e : p->ev)
@@ -478,7 +508,7 @@ static int plan_free(SonicPlan* p) {
 template <int NID>
 static void launch_average(SonicPlan* p, int blocks) {
     sonic_average_kernel<NID><<<blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(
-        p->d_zbuf, p->d_ia, p->d_Q, p->d_radii, p->d_status, p->n, p->d_fs, p->nfs, p->d_out);
+        p->d_zbuf, p->d_ia, p->d_Q, p->d_radii, p->d_status, p->n, p->d_fs, p->nfs, p->nov, p->d_ov, p->d_out);
 }
 
 template <int NID>
@@ -573,6 +603,13 @@ int sonic_mean_rates(int device, int id, const double* Vm, int64_t n, double* ou
 int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
                       const int32_t* ia, const double* f, const double* A, const double* Q,
                       const double* fs, int nfs, SonicPlan** out_plan) {
+    return sonic_plan_create_ex(device, radii, na, neuron_id, n, ia, f, A, Q, 0, nullptr, fs, nfs, out_plan);
+}
+
+int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                         const int32_t* ia, const double* f, const double* A, const double* Q,
+                         int novertones, const double* overtones, const double* fs, int nfs,
+                         SonicPlan** out_plan) {
     int rc = check_device(device);
     if (rc) return rc;
     if (neuron_id < 0 || neuron_id >= SONIC_N_NEURONS)
@@ -580,6 +617,8 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     if (!radii || na <= 0 || n <= 0 || !ia || !f || !A || !Q || !fs || nfs <= 0 || !out_plan)
         return set_err(SONIC_E_ARG, "invalid argument (null pointer or empty dimension)");
     if (n > 0x7fffffffLL) return set_err(SONIC_E_ARG, "too many points for one plan (%lld)", (long long)n);
+    if (novertones < 0 || novertones > SONIC_MAX_OVERTONES || (novertones > 0 && !overtones))
+        return set_err(SONIC_E_ARG, "invalid charge overtones (0..%d per point, array required)", SONIC_MAX_OVERTONES);
     for (int64_t i = 0; i < n; i++) {
         if (ia[i] < 0 || ia[i] >= na) return set_err(SONIC_E_ARG, "radius index out of range at point %lld", (long long)i);
         if (!(f[i] > 0.)) return set_err(SONIC_E_ARG, "frequency must be strictly positive (point %lld)", (long long)i);
@@ -603,6 +642,8 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     p->na = na;
     p->nfs = nfs;
     p->n = n;
+    p->nov = novertones;
+    p->nvar = 1 + 2 * novertones + p->nrates;
 
     // launch geometry of the persistent integrator
     cudaDeviceProp prop;
@@ -655,7 +696,10 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     TRYA(pool_take(device, 0, p->zbuf_count, &p->d_zbuf));
     TRYA(pool_take(device, 1, p->ngbuf_count, &p->d_ngbuf));
     TRYA(dalloc(&p->d_tpoint, n));
-    TRYA(dalloc(&p->d_out, (size_t)(1 + p->nrates) * n * nfs));
+    TRYA(dalloc(&p->d_out, (size_t)p->nvar * n * nfs));
+    TRYA(dalloc(&p->d_ov, (size_t)n * 2 * std::max(novertones, 1)));
+    if (novertones > 0)
+        TRYA(cudaMemcpyAsync(p->d_ov, overtones, (size_t)n * 2 * novertones * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     TRYA(dalloc(&p->d_status, n)); TRYA(dalloc(&p->d_nfe, n)); TRYA(dalloc(&p->d_nje, n));
     TRYA(dalloc(&p->d_nsteps, n)); TRYA(dalloc(&p->d_counter, 1));
     const int warps_per_block = SONIC_BLOCK / 32;
@@ -687,7 +731,7 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
             SonicJob zj;
             memset(&zj, 0, sizeof(zj));
             zj.radii = p->d_radii; zj.ia = p->d_ia; zj.f = p->d_f; zj.A = p->d_A; zj.Q = p->d_Q;
-            zj.z0 = p->d_z0; zj.n = p->n;
+            zj.z0 = p->d_z0; zj.n = p->n; zj.ov = p->d_ov; zj.nov = p->nov;
             sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(zj);
         }
         sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
@@ -775,7 +819,7 @@ int sonic_plan_launch(SonicPlan* p) {
     CUDA_TRY(cudaSetDevice(p->device));
     SonicJob job;
     job.radii = p->d_radii; job.order = p->d_order; job.ia = p->d_ia; job.f = p->d_f; job.A = p->d_A;
-    job.Q = p->d_Q; job.z0 = p->d_z0; job.zbuf = p->d_zbuf; job.ngbuf = p->d_ngbuf;
+    job.Q = p->d_Q; job.ov = p->d_ov; job.nov = p->nov; job.z0 = p->d_z0; job.zbuf = p->d_zbuf; job.ngbuf = p->d_ngbuf;
     job.ncycles = p->d_ncycles; job.status = p->d_status; job.nfe = p->d_nfe; job.nje = p->d_nje;
     job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
     job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
@@ -841,7 +885,7 @@ int sonic_plan_fetch(SonicPlan* p, double* out_tables, int32_t* out_ncycles, uin
     CUDA_TRY(cudaSetDevice(p->device));
     const size_t n = p->n;
     if (out_tables)
-        CUDA_TRY(cudaMemcpyAsync(out_tables, p->d_out, (size_t)(1 + p->nrates) * n * p->nfs * sizeof(double),
+        CUDA_TRY(cudaMemcpyAsync(out_tables, p->d_out, (size_t)p->nvar * n * p->nfs * sizeof(double),
                                  cudaMemcpyDeviceToHost, p->stream));
     if (out_ncycles)
         CUDA_TRY(cudaMemcpyAsync(out_ncycles, p->d_ncycles, n * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
@@ -919,12 +963,21 @@ int sonic_points_run(int device, const SonicBlsParams* radii, int na, int neuron
                      const int32_t* ia, const double* f, const double* A, const double* Q,
                      const double* fs, int nfs, double* out_tables, int32_t* out_ncycles,
                      uint32_t* out_status, double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats) {
+    return sonic_points_run_ex(device, radii, na, neuron_id, n, ia, f, A, Q, 0, nullptr, fs, nfs, out_tables,
+                               out_ncycles, out_status, out_tpoint, out_nrhs, stats);
+}
+
+int sonic_points_run_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
+                        const int32_t* ia, const double* f, const double* A, const double* Q,
+                        int novertones, const double* overtones, const double* fs, int nfs,
+                        double* out_tables, int32_t* out_ncycles, uint32_t* out_status,
+                        double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats) {
     const auto t0 = std::chrono::steady_clock::now();
     auto ms_since = [&](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
     };
     SonicPlan* p = nullptr;
-    int rc = sonic_plan_create(device, radii, na, neuron_id, n, ia, f, A, Q, fs, nfs, &p);
+    int rc = sonic_plan_create_ex(device, radii, na, neuron_id, n, ia, f, A, Q, novertones, overtones, fs, nfs, &p);
     if (rc) return rc;
     const double ms_create = ms_since(t0);
     rc = sonic_plan_launch(p);

@@ -65,6 +65,7 @@
 #define SONIC_NOUT 999         /* new samples appended per cycle (solvers.py:168-170) */
 #define SONIC_NCYC_CAP 11      /* solvers.py:353-359 with NCYCLES_MAX = 10 */
 #define SONIC_MXSTEP 500       /* LSODA default, odeint passes mxstep = 0 */
+#define SONIC_MAX_OVERTONES 4  /* charge Fourier overtones per point (nbls.py:169-178) */
 
 // status bits reported per point
 #define SONIC_ST_OK 0u
@@ -136,11 +137,18 @@ struct SonicPoint {
     double pel0;               // Q^2 / (2 eps0 epsR)
     double omega;              // 2 pi f
     double f;
+    // imposed charge Q(t) = Qm_cycle[int((t mod T) / dt)] with a Fourier-series cycle
+    // (nbls.py:169-178, bls.py:763-768); nov = 0: constant charge
+    double q0;                 // mean charge Qm0 (C/m2)
+    const double* ov;          // [nov][2]: overtone amplitudes (C/m2) and phases (rad)
+    int nov;
+    int jq;                    // sample index pel0 currently stands for
     double A;
     double ng0;
 };
 
-SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, double A, double Q) {
+SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, double A, double Q,
+                               int nov = 0, const double* ov = nullptr) {
     p.a = b.a;
     p.a2 = b.a * b.a;
     p.inva2 = 1.0 / p.a2;
@@ -161,6 +169,10 @@ SONIC_HD void sonic_point_init(SonicPoint& p, const SonicBls& b, double f, doubl
     p.f = f;
     p.A = A;
     p.ng0 = SONIC_P0 * p.V0 / (SONIC_RG * SONIC_T);     // bls.py:137,529-536
+    p.q0 = Q;
+    p.nov = nov;
+    p.ov = ov;
+    p.jq = -1;
 }
 
 // Reciprocal: hardware seed + Newton refinement on the device (<= 1 ulp), exact division on the
@@ -336,6 +348,21 @@ SONIC_HD double sonic_sin_drive(double u) {
     return -(th * poly);
 }
 
+// Sample j (0..999) of the imposed charge cycle: numpy.fft.irfft([Q0, A_k exp(i phi_k)], 1000) * 1000
+// = Q0 + 2 sum_k A_k cos(2 pi j k / 1000 + phi_k)   (nbls.py:174-177).
+SONIC_HD double sonic_charge_sample(double q0, int nov, const double* ov, int j) {
+    double q = q0;
+    for (int k = 0; k < nov; k++) {
+        // cos(2 pi x) = sin(2 pi (x + 1/4)) = -sin_drive(x + 1/4)
+        const double x = (double)((j * (k + 1)) % SONIC_NPC) * (1.0 / SONIC_NPC) + ov[2 * k + 1] * 0.15915494309189535;
+        q -= 2.0 * ov[2 * k] * sonic_sin_drive(x + 0.25);
+    }
+    return q;
+}
+
+// Index of the charge sample in force at time t: int((t mod T) / dt), T = 1 / f, dt = T / 1000
+// (bls.py:766-768), and the matching electrical pressure factor.
+
 // d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).  The heuristics
 // only steer the step size (the result is clipped, thresholded at 10 % and multiplied by safety
 // factors), so on the device the power goes through the single-precision log2/exp2 units
@@ -426,6 +453,19 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     dy[2] = SONIC_DIVC(2.0 * (SONIC_PI * s2) * SONIC_DGL * (SONIC_C0 - SONIC_DIVC(Pg, SONIC_KH)),
                        SONIC_XI);                                    // bls.py:508-516
     return clamped;
+}
+
+// Refresh the electrical pressure factor Q(t)^2 / (2 eps0) of a point with charge overtones.
+SONIC_HD void sonic_update_charge(SonicPoint& p, double t) {
+    const double T = 1.0 / p.f;
+    const double dt = 1.0 / (SONIC_NPC * p.f);
+    int j = (int)(fmod(t, T) / dt);
+    if (j >= SONIC_NPC) j = SONIC_NPC - 1;
+    if (j != p.jq) {
+        const double q = sonic_charge_sample(p.q0, p.nov, p.ov, j);
+        p.pel0 = q * q / (2.0 * (SONIC_EPS0 * 1.0));
+        p.jq = j;
+    }
 }
 
 // Jacobian columns for the U and ng perturbations of a finite-difference Jacobian, as exact

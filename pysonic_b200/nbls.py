@@ -39,14 +39,23 @@ class NeuronalBilayerSonophore(BilayerSonophore):
     def __repr__(self):
         return f'{self.__class__.__name__}({self.a * 1e9:.1f} nm, {self.pneuron})'
 
-    def effvars_batch(self, f, A, Q, fs, device=0):
+    def effvars_batch(self, f, A, Q, fs, device=0, overtones=None):
         ''' Effective variables for arrays of points (same radius).
-            :return: (tables[1+nrates, n, nfs], ncycles, status, tpoint, nrhs, stats) '''
+            :param overtones: None, or charge overtones [n, novertones, 2] (amplitude C/m2, phase rad)
+            :return: (tables[1+2*novertones+nrates, n, nfs], ncycles, status, tpoint, nrhs, stats) '''
         f, A, Q = np.broadcast_arrays(np.asarray(f, float), np.asarray(A, float), np.asarray(Q, float))
         fs = np.atleast_1d(np.asarray(fs, float))
         ia = np.zeros(f.size, dtype=np.int32)
         return _lib.points_run(device, [self.abi_params()], self.pneuron.neuron_id,
-                               len(self.pneuron.rates), ia, f.ravel(), A.ravel(), Q.ravel(), fs)
+                               len(self.pneuron.rates), ia, f.ravel(), A.ravel(), Q.ravel(), fs,
+                               overtones=overtones)
+
+    def effvars_keys(self, novertones=0):
+        ''' Key order of the effective-variable dictionaries (nbls.py:191-204). '''
+        keys = ['V']
+        for i in range(1, novertones + 1):
+            keys += [f'A_V{i}', f'phi_V{i}']
+        return keys + self.pneuron.rates
 
     def computeEffVars(self, drive, fs, Qm0, Qm_overtones=None):
         ''' Effective coefficients for one acoustic drive and charge density
@@ -56,16 +65,19 @@ class NeuronalBilayerSonophore(BilayerSonophore):
             :param drive: acoustic drive object
             :param fs: sonophore membrane coverage fraction(s)
             :param Qm0: imposed charge density (C/m2)
-            :return: (list of one {V, rates...} dict per fs, computation time in s)
+            :param Qm_overtones: optional list of (amplitude C/m2, phase rad) pairs: the imposed
+                charge is then the Fourier-series cycle of nbls.py:173-178
+            :return: (list of one {V, [A_Vk, phi_Vk...], rates...} dict per fs, computation time in s)
         '''
+        ov = None
         if Qm_overtones is not None:
-            raise NotImplementedError('charge overtones are not supported by the GPU engine yet')
+            ov = np.asarray(Qm_overtones, dtype=float).reshape(1, -1, 2)
         if not isinstance(drive, AcousticDrive) and not (hasattr(drive, 'f') and hasattr(drive, 'A')):
             raise TypeError('Invalid "drive" parameter (must be an "AcousticDrive" object)')
         t0 = time.perf_counter()
         fs = np.atleast_1d(np.asarray(fs, dtype=float))
-        out, ncyc, status, _, _, _ = self.effvars_batch(drive.f, drive.A, float(Qm0), fs)
-        keys = ['V'] + self.pneuron.rates
+        out, ncyc, status, _, _, _ = self.effvars_batch(drive.f, drive.A, float(Qm0), fs, overtones=ov)
+        keys = self.effvars_keys(0 if ov is None else ov.shape[1])
         effvars_list = [{k: out[i, 0, j] for i, k in enumerate(keys)} for j in range(fs.size)]
         if status[0] & 1:
             logger.warning('%s: periodic criterion not met -> stopped after %d cycles', self, ncyc[0])

@@ -73,12 +73,14 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
         for x in ['a', 'f']:
             assert len(refs[x]) == 1, err_span.format(_DESCS['fs'], _DESCS[x])
     refs['fs'] = fsref
-    if novertones > 0:
-        raise NotImplementedError('charge overtones are not supported by the GPU engine yet')
+    if novertones > _lib_max_overtones():
+        raise ValueError(f'at most {_lib_max_overtones()} charge overtones are supported')
     if test:
         refs = {k: np.array([v.min(), v.max()]) if v.size > 1 else v for k, v in refs.items()}
     _validate(refs)
     refs = {k: np.asarray(v, dtype=np.float64) for k, v in refs.items()}
+    if novertones > 0:
+        return _overtones_lookup(pneuron, refs, novertones, test, loglevel, return_info, device)
     dims = tuple(x.size for x in refs.values())
     na, nf, nA, nQ, nfs = dims
     keys = ['V'] + pneuron.rates
@@ -126,6 +128,55 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
     lkp = Lookup(refs, tables)
     if return_info:
         return lkp, {'ncycles': ncyc, 'status': status, 'stats': stats, 'wall_s': wall}
+    return lkp
+
+
+def _lib_max_overtones():
+    return 4     # SONIC_MAX_OVERTONES of the native library
+
+
+def _overtones_lookup(pneuron, refs, novertones, test, loglevel, return_info, device):
+    ''' Lookup with charge overtones (run_lookups.py:105-128): every (a, f, A, Q) point is
+        combined with every (AQ1, phiQ1, ..., AQn, phiQn) combination; the overtone dimensions come
+        after Q and before fs, and every overtone adds the tables A_Vk, phi_Vk after V. '''
+    nAQ, nphiQ = 5, 5
+    AQ_ref = np.linspace(0, 100e-5, nAQ)                          # C/m2
+    phiQ_ref = np.linspace(0, 2 * np.pi, nphiQ, endpoint=False)   # rad
+    if test:
+        AQ_ref = np.array([AQ_ref.min(), AQ_ref.max()])
+        phiQ_ref = np.array([phiQ_ref.min(), phiQ_ref.max()])
+    fsref = refs.pop('fs')
+    for i in range(novertones):
+        refs[f'AQ{i + 1}'] = AQ_ref
+        refs[f'phiQ{i + 1}'] = phiQ_ref
+    refs['fs'] = fsref
+    dims = tuple(x.size for x in refs.values())
+    na = dims[0]
+    grids = np.meshgrid(np.arange(na), *[refs[k] for k in list(refs)[1:-1]], indexing='ij')
+    ia = grids[0].ravel().astype(np.int32)
+    f, A, Q = (g.ravel() for g in grids[1:4])
+    ov = np.stack([g.ravel() for g in grids[4:]], axis=1).reshape(ia.size, novertones, 2)
+    nrates = len(pneuron.rates)
+    bls_params = [NeuronalBilayerSonophore(float(a), pneuron).abi_params() for a in refs['a']]
+    logger.log(loglevel, 'Starting lookup batch for %s neuron: %d points (%d charge overtones) x %d fs',
+               pneuron.name, ia.size, novertones, dims[-1])
+    t0 = time.perf_counter()
+    dev = dist_info()[2] if device is None else int(device)
+    out, ncyc, status, tpoint, nrhs, stats = _lib.points_run(
+        dev, bls_params, pneuron.neuron_id, nrates, ia, f, A, Q, refs['fs'], overtones=ov)
+    wall = time.perf_counter() - t0
+    logger.log(loglevel, 'Lookup batch completed in %.3f s', wall)
+    keys = ['V']
+    for i in range(1, novertones + 1):
+        keys += [f'A_V{i}', f'phi_V{i}']
+    keys += pneuron.rates
+    tables = {k: np.ascontiguousarray(out[i].reshape(dims)) for i, k in enumerate(keys)}
+    tp = tpoint.reshape(dims[:-1])
+    tables['tcomp'] = np.ascontiguousarray(np.moveaxis(np.array([tp for _ in range(dims[-1])]), 0, -1))
+    lkp = Lookup(refs, tables)
+    if return_info:
+        return lkp, {'ncycles': ncyc.reshape(dims[:-1]), 'status': status.reshape(dims[:-1]), 'stats': stats,
+                     'wall_s': wall}
     return lkp
 
 

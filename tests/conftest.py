@@ -64,7 +64,10 @@ class HostSim:
     def _bls(self, b):
         return np.array([b.a, b.Delta, b.x0, b.C, b.nrep, b.nattr, b.Cm0, 0.0])
 
-    def point(self, b, f, A, Q, trace=False):
+    def point(self, b, f, A, Q, trace=False, overtones=None):
+        ''' overtones: list of (amplitude C/m2, phase rad) pairs (nbls.py:169-178) '''
+        if overtones:
+            return self._point_ov(b, f, A, Q, overtones)
         bls = self._bls(b)
         z, ng = np.zeros(1000), np.zeros(1000)
         ncyc, st = ctypes.c_int(), ctypes.c_uint()
@@ -78,6 +81,29 @@ class HostSim:
             ctypes.c_long(tr.shape[0] if trace else 0), ctypes.byref(nrows))
         return {'z': z, 'ng': ng, 'ncycles': ncyc.value, 'status': st.value, 'nfe': stats[0],
                 'nje': stats[1], 'nsteps': stats[2], 'trace': tr[:nrows.value] if trace else None}
+
+    def _point_ov(self, b, f, A, Q, overtones):
+        bls = self._bls(b)
+        ov = np.ascontiguousarray(np.asarray(overtones, float).reshape(-1, 2))
+        z, ng = np.zeros(1000), np.zeros(1000)
+        ncyc, st = ctypes.c_int(), ctypes.c_uint()
+        stats = (ctypes.c_uint * 3)()
+        nrows = ctypes.c_long()
+        self.lib.hostsim_point_ov.restype = ctypes.c_long
+        self.lib.hostsim_point_ov(
+            bls.ctypes.data_as(self.dp), ctypes.c_double(f), ctypes.c_double(A), ctypes.c_double(Q),
+            ctypes.c_int(ov.shape[0]), ov.ctypes.data_as(self.dp), z.ctypes.data_as(self.dp),
+            ng.ctypes.data_as(self.dp), ctypes.byref(ncyc), ctypes.byref(st), stats, None, ctypes.c_long(0),
+            ctypes.byref(nrows))
+        return {'z': z, 'ng': ng, 'ncycles': ncyc.value, 'status': st.value, 'nfe': stats[0],
+                'nje': stats[1], 'nsteps': stats[2], 'trace': None}
+
+    def charge_cycle(self, q0, overtones):
+        ov = np.ascontiguousarray(np.asarray(overtones, float).reshape(-1, 2))
+        self.lib.hostsim_charge_sample.restype = ctypes.c_double
+        return np.array([self.lib.hostsim_charge_sample(ctypes.c_double(q0), ctypes.c_int(ov.shape[0]),
+                                                        ov.ctypes.data_as(self.dp), ctypes.c_int(j))
+                         for j in range(1000)])
 
     def rhs(self, b, f, A, Q, t, y):
         bls = self._bls(b)

@@ -250,6 +250,32 @@ def gen_c2sub(amp_scale=1.0, tag=''):
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
 
 
+def _ov_point(args):
+    name, a, f, A, Q, fs, ov = args
+    _counters['ncycles'] = 0
+    ev, tcomp = _nbls(name, a).computeEffVars(AcousticDrive(f, A), np.array(fs), Q, ov)
+    return {'effvars': [{k: float(v) for k, v in e.items()} for e in ev], 'ncycles': _counters['ncycles'], 'tcomp': tcomp}
+
+
+def gen_overtones():
+    ''' Charge-overtone variant of computeEffVars (nbls.py:169-201, run_lookups.py:105-128):
+        RS, 32 nm, 500 kHz, sub-grid of (A, Q, AQ1, phiQ1) plus one two-overtone point. '''
+    A = [50e3, 300e3]
+    Q = [-80e-5, -20e-5, 30e-5]
+    AQ = [0., 50e-5, 100e-5]
+    phi = [0., 2 * np.pi / 5, 6 * np.pi / 5]
+    jobs = [('RS', 32e-9, 500e3, a_, q_, [1.0], [(aq, ph)]) for a_ in A for q_ in Q for aq in AQ for ph in phi]
+    jobs.append(('RS', 32e-9, 500e3, 100e3, -71.9e-5, [0.5, 1.0], [(50e-5, 1.0), (25e-5, 4.0)]))
+    with mp.get_context('fork').Pool(mp.cpu_count()) as pool:
+        recs = pool.map(_ov_point, jobs, chunksize=1)
+    out = {'grid': {'neuron': 'RS', 'a': 32e-9, 'f': 500e3, 'A': A, 'Q': Q, 'AQ1': AQ, 'phiQ1': phi, 'fs': [1.0]},
+           'points': [dict(neuron=j[0], a=j[1], f=j[2], A=j[3], Q=j[4], fs=j[5], overtones=[list(x) for x in j[6]], **r)
+                      for j, r in zip(jobs, recs)]}
+    with open(os.path.join(HERE, 'overtones.json'), 'w') as fh:
+        json.dump(out, fh, indent=1)
+    print('overtones.json:', len(jobs), 'points')
+
+
 def _cm_point(args):
     a, f, A, Qm = args
     from PySONIC.core import BilayerSonophore
@@ -285,9 +311,9 @@ def gen_noise():
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
-            'c2sub': gen_c2sub, 'cm': gen_cm, 'noise': gen_noise,
+            'c2sub': gen_c2sub, 'cm': gen_cm, 'overtones': gen_overtones, 'noise': gen_noise,
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k != 'noise_neurons'):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm')):
             fn()

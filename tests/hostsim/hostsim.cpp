@@ -29,9 +29,10 @@ long hostsim_steplog_rows(void) { return g_steplog_n; }
 // trace (optional, may be NULL): rows of 8 doubles per emitted sample
 //   [cycle, k, nst, nfe_in_cycle, nje_in_cycle, hu, tn, nqu*10 + mused]
 // returns number of ticks executed
-long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf, double* ngbuf,
-                   int* ncycles, unsigned* status, unsigned* stats, double* trace,
-                   long trace_rows_max, long* trace_rows) {
+// same with charge overtones: ov = [nov][2] (amplitude C/m2, phase rad)
+long hostsim_point_ov(const double* bls, double f, double A, double Q, int nov, const double* ov,
+                      double* zbuf, double* ngbuf, int* ncycles, unsigned* status, unsigned* stats,
+                      double* trace, long trace_rows_max, long* trace_rows) {
     if (!g_tab_ready) {
         sonic_fill_tables(&g_tab);
         g_tab_ready = 1;
@@ -40,7 +41,8 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     b.a = bls[0]; b.Delta = bls[1]; b.x0 = bls[2]; b.C = bls[3]; b.nrep = bls[4];
     b.nattr = bls[5]; b.Cm0 = bls[6]; b.depth = bls[7];
     SonicPoint p;
-    sonic_point_init(p, b, f, A, Q);
+    sonic_point_init(p, b, f, A, Q, nov, ov);
+    if (p.nov) sonic_update_charge(p, 0.0);
     SonicSink sink;
     sink.zbuf = zbuf; sink.ngbuf = ngbuf;
     SonicLane s;
@@ -57,6 +59,7 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
     unsigned nfe_base = 0, nje_base = 0;
     while (s.phase != PH_DONE) {
         double fv[3];
+        if (p.nov) sonic_update_charge(p, s.tn);
         if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
         sonic_tick(s, H, &g_tab, p, sink, period, fv, 0u);
         nticks++;
@@ -95,6 +98,18 @@ long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf
 void hostsim_math(int kind, const double* x, double* out, long n) {
     for (long i = 0; i < n; i++)
         out[i] = kind == 0 ? sonic_log(x[i]) : kind == 1 ? sonic_exp(x[i]) : kind == 2 ? sonic_sin_drive(x[i]) : sonic_rcp(x[i]);
+}
+
+long hostsim_point(const double* bls, double f, double A, double Q, double* zbuf, double* ngbuf,
+                   int* ncycles, unsigned* status, unsigned* stats, double* trace,
+                   long trace_rows_max, long* trace_rows) {
+    return hostsim_point_ov(bls, f, A, Q, 0, 0, zbuf, ngbuf, ncycles, status, stats, trace, trace_rows_max,
+                            trace_rows);
+}
+
+// charge cycle sample j of a Fourier-series charge (nbls.py:174-177)
+double hostsim_charge_sample(double q0, int nov, const double* ov, int j) {
+    return sonic_charge_sample(q0, nov, ov, j);
 }
 
 void hostsim_rhs(const double* bls, double f, double A, double Q, double t, const double* y,

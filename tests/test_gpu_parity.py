@@ -101,8 +101,6 @@ def test_computeEffVars_signature(gpu):
     # Appendix A of SURVEY.md (reference run): V = -136.787 mV at fs = 1, -85.944 mV at fs = 0.5
     assert effvars[1]['V'] == pytest.approx(-136.78744984747215, rel=RTOL)
     assert effvars[0]['V'] == pytest.approx(-85.94358404646884, rel=RTOL)
-    with pytest.raises(NotImplementedError):
-        nbls.computeEffVars(ps.AcousticDrive(500e3, 100e3), 1.0, -71.9e-5, Qm_overtones=np.zeros((1, 2)))
     with pytest.raises(TypeError):
         nbls.computeEffVars('drive', 1.0, -71.9e-5)
 
@@ -408,3 +406,77 @@ def test_cm_lookup(gpu, tmp_path):
     with open(fpath, 'rb') as fh:
         d = pickle.load(fh)
     assert list(d['refs']) == ['f', 'A', 't'] and d['tables']['Cm_rel'].shape == (3, 4, 1000)
+
+
+@pytest.fixture(scope='module')
+def overtones_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'overtones.json')) as fh:
+        return json.load(fh)
+
+
+def test_charge_overtones_points(gpu, overtones_golden):
+    ''' computeEffVars(drive, fs, Qm0, Qm_overtones) (nbls.py:169-201) against the
+        reference on a (A, Q, AQ1, phiQ1) sub-grid and a two-overtone point: V, A_Vk, phi_Vk, rates. '''
+    ps = _ps()
+    pts = overtones_golden['points']
+    nbls = ps.NeuronalBilayerSonophore(32e-9, ps.getPointNeuron('RS'))
+    single = [p for p in pts if len(p['overtones']) == 1]
+    f = np.array([p['f'] for p in single]); A = np.array([p['A'] for p in single])
+    Q = np.array([p['Q'] for p in single]); ov = np.array([p['overtones'] for p in single])
+    out, ncyc, status, _, _, _ = nbls.effvars_batch(f, A, Q, [1.0], overtones=ov)
+    keys = nbls.effvars_keys(1)
+    assert keys[:3] == ['V', 'A_V1', 'phi_V1'] and out.shape == (len(keys), len(single), 1)
+    bad = 0
+    for n, p in enumerate(single):
+        ref = p['effvars'][0]
+        assert list(ref.keys()) == keys
+        e = 0.0
+        for i, k in enumerate(keys):
+            if k.startswith('phi_V'):
+                d = abs((out[i, n, 0] - ref[k] + np.pi) % (2 * np.pi) - np.pi)      # phases: absolute, mod 2 pi
+                e = max(e, d if ref['A_V1'] > 1e-6 else 0.0)
+            else:
+                e = max(e, float(rel_err(out[i, n, 0], ref[k])))
+        bad += (e > RTOL) or (ncyc[n] != p['ncycles']) or status[n] != 0
+    assert bad <= 2, bad          # the staircase charge makes a few points as noisy as the low-amplitude regime
+    # two overtones, two coverage fractions, through the reference-signature method
+    p = [q for q in pts if len(q['overtones']) == 2][0]
+    effvars, tcomp = nbls.computeEffVars(ps.AcousticDrive(p['f'], p['A']), np.array(p['fs']), p['Q'],
+                                         [tuple(x) for x in p['overtones']])
+    assert len(effvars) == 2 and list(effvars[0].keys()) == nbls.effvars_keys(2)
+    for ev, ref in zip(effvars, p['effvars']):
+        for k in ref:
+            if k.startswith('phi_V'):
+                assert abs((ev[k] - ref[k] + np.pi) % (2 * np.pi) - np.pi) < 1e-4, k
+            else:
+                assert rel_err(ev[k], ref[k]) <= RTOL, (k, ev[k], ref[k])
+
+
+def test_charge_overtones_lookup_layout(gpu):
+    ''' computeAStimLookup(novertones=1): overtone dimensions between Q and fs, tables A_V1 / phi_V1 after V
+        (run_lookups.py:105-128,161-167); Batch with the reference's (args, kwargs) queue items. '''
+    ps = _ps()
+    from pysonic_b200.batches import Batch
+    pn = ps.getPointNeuron('RS')
+    lkp = ps.computeAStimLookup(pn, np.array([32e-9]), np.array([2e6]), np.array([5e4, 1e5]), np.array([1.0]),
+                                np.array([-5e-4, 0., 3e-4]), novertones=1, test=True, loglevel=10)
+    assert list(lkp.refs) == ['a', 'f', 'A', 'Q', 'AQ1', 'phiQ1', 'fs']
+    assert list(lkp.tables) == ['V', 'A_V1', 'phi_V1'] + pn.rates + ['tcomp']
+    assert lkp['V'].shape == (1, 1, 2, 2, 2, 2, 1)
+    np.testing.assert_allclose(lkp.refs['AQ1'], [0., 100e-5])
+    # zero overtone amplitude = the plain lookup, whatever the phase
+    plain = ps.computeAStimLookup(pn, np.array([32e-9]), np.array([2e6]), np.array([5e4, 1e5]), np.array([1.0]),
+                                  np.array([-5e-4, 3e-4]), loglevel=10)
+    for k in ['V'] + pn.rates:
+        np.testing.assert_allclose(lkp[k][:, :, :, :, 0, 0, :], plain[k], rtol=1e-9)
+        np.testing.assert_array_equal(lkp[k][:, :, :, :, 0, 0, :], lkp[k][:, :, :, :, 0, 1, :])
+    # (A_V1 does not vanish with AQ1: the capacitance oscillation alone modulates V at the drive frequency)
+    assert np.all(lkp['A_V1'] >= 0) and np.all(np.abs(lkp['phi_V1']) <= np.pi)
+    nbls = ps.NeuronalBilayerSonophore(32e-9, pn)
+    drive = ps.AcousticDrive(2e6, 1e5)
+    queue = [([drive, np.array([1.0]), 3e-4], {'Qm_overtones': [(100e-5, 0.0)]}),
+             ([drive, np.array([1.0]), -5e-4], {'Qm_overtones': [(0.0, 0.0)]})]
+    outs = Batch(nbls.computeEffVars, queue)(mpi=True, loglevel=10)
+    assert outs[0][0][0]['V'] == lkp['V'][0, 0, 1, 1, 1, 0, 0]
+    assert outs[1][0][0]['A_V1'] == lkp['A_V1'][0, 0, 1, 0, 0, 0, 0]

@@ -80,8 +80,8 @@ def test_grid_validation_mirrors_reference():
         ps.computeAStimLookup(pn, a, f, np.array([-1.]), fs, Q)              # negative amplitude
     with pytest.raises(AssertionError):
         ps.computeAStimLookup(pn, a, np.array([1e5, 5e5]), A, np.array([0.5, 1.]), Q)   # fs sweep, 2 f
-    with pytest.raises(NotImplementedError):
-        ps.computeAStimLookup(pn, a, f, A, fs, Q, novertones=1)
+    with pytest.raises(ValueError):
+        ps.computeAStimLookup(pn, a, f, A, fs, Q, novertones=9)                # more overtones than supported
     _validate({'a': list(a), 'f': list(f), 'A': list(A), 'Q': list(Q), 'fs': list(fs)})
 
 

@@ -194,3 +194,39 @@ def test_capacitance_profiles_pointwise(hostsim):
             cm = so.v_capacitance(b, h['z']) / b.Cm0
             dev = np.abs(cm - g['Cm_rel'][i, j]) / g['Cm_rel'][i, j]
             assert dev.max() <= 2e-4 and dev.mean() <= 2e-5, (f, A, dev.max(), dev.mean())
+
+
+def test_charge_overtones(hostsim):
+    ''' Lane machine with a Fourier-series charge (nbls.py:169-201): the charge cycle against
+        numpy's irfft, then every golden overtone point against the reference. '''
+    import json
+    import os
+    ov = [(50e-5, 1.0), (25e-5, 4.0)]
+    A_Qm, phi = zip(*ov)
+    ref = np.fft.irfft(np.hstack(([-71.9e-5 + 0j], np.array(A_Qm) * (np.cos(phi) + 1j * np.sin(phi)))), n=1000) * 1000
+    assert np.max(np.abs(hostsim.charge_cycle(-71.9e-5, ov) - ref)) < 1e-17
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'overtones.json')) as fh:
+        pts = json.load(fh)['points']
+    b = so.get_bls('RS', 32e-9)
+    bad = 0
+    for p in pts:
+        ovp = [tuple(x) for x in p['overtones']]
+        h = hostsim.point(b, p['f'], p['A'], p['Q'], overtones=ovp)
+        Qc = hostsim.charge_cycle(p['Q'], ovp)
+        Cm = so.v_capacitance(b, h['z'])
+        e = 0.0
+        for fs, refev in zip(p['fs'], p['effvars']):
+            Vm = Qc / (fs * Cm + (1 - fs) * b.Cm0) * 1e3
+            c = np.fft.rfft(Vm)[:len(ovp) + 1] / 1000
+            ev = {'V': np.mean(Vm)}
+            for i in range(1, len(ovp) + 1):
+                ev[f'A_V{i}'], ev[f'phi_V{i}'] = abs(c[i]), np.angle(c[i])
+            ev.update(so.eff_rates('RS', Vm))
+            for k in refev:
+                if k.startswith('phi_V'):
+                    d = abs((ev[k] - refev[k] + np.pi) % (2 * np.pi) - np.pi)
+                    e = max(e, d if refev['A_V' + k[5:]] > 1e-6 else 0.0)
+                else:
+                    e = max(e, float(rel_err(ev[k], refev[k])))
+        bad += (e > RTOL) or (h['ncycles'] != p['ncycles']) or h['status'] != 0
+    assert bad <= 2, bad

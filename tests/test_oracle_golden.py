@@ -88,3 +88,22 @@ def test_relative_capacitance_profiles():
     refs, tables = so.compute_cm_lookup(b, g['f'][2:], g['A'][:2])
     assert list(refs) == ['f', 'A', 't'] and tables['Cm_rel'].shape == (1, 2, 1000)
     np.testing.assert_array_equal(refs['t'], g['t'])
+
+
+def test_charge_overtones_points():
+    ''' compute_effvars(..., Qm_overtones) (nbls.py:169-201, bls.py:766-768) against the reference:
+        two of the golden points (each costs seconds: the staircase charge makes LSODA restart
+        a thousand times per cycle). '''
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'overtones.json')) as fh:
+        pts = json.load(fh)['points']
+    b = so.get_bls('RS', 32e-9)
+    for p in (pts[4], pts[-1]):
+        ev, ncyc = so.compute_effvars('RS', b, p['f'], p['A'], p['fs'], p['Q'],
+                                      Qm_overtones=[tuple(x) for x in p['overtones']])
+        assert ncyc == p['ncycles']
+        for mine, ref in zip(ev, p['effvars']):
+            assert list(mine.keys()) == list(ref.keys())
+            for k in ref:
+                assert mine[k] == pytest.approx(ref[k], rel=TOL, abs=1e-300), k
