@@ -73,7 +73,8 @@ typedef struct {
 
 /* Aggregate statistics of one run (all devices summed unless noted). */
 typedef struct {
-    uint64_t n_points;      /* ODE points integrated */
+    uint64_t n_points;      /* output points; the counters below cover the trajectories actually
+                             * integrated (points that differ by the sign of Q share one) */
     uint64_t n_rhs;         /* right-hand-side evaluations (integrator ticks) */
     uint64_t n_jac;         /* finite-difference Jacobian evaluations */
     uint64_t n_steps;       /* accepted integrator steps */

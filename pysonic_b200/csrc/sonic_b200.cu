@@ -27,6 +27,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #define SONIC_BLOCK 128
@@ -237,21 +238,23 @@ sonic_average_kernel(const double* __restrict__ zbuf, const int* __restrict__ ia
                      const double* __restrict__ Q, const SonicBls* __restrict__ radii,
                      const unsigned* __restrict__ status, long long n,
                      const double* __restrict__ fs, int nfs, int nov, const double* __restrict__ ov,
-                     double* __restrict__ out) {
+                     const int* __restrict__ umap, double* __restrict__ out) {
     constexpr int NR = SonicRates<NID>::N;
     constexpr int NV = 1 + 2 * SONIC_MAX_OVERTONES + NR;
     __shared__ double cm_s[SONIC_AVG_WARPS][SONIC_NPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nwarps = (long long)gridDim.x * SONIC_AVG_WARPS;
     const int nvar = 1 + 2 * nov + NR;          // V, (A_Vk, phi_Vk) per overtone, rates
+    // n = output points, Q = their signed charges; u = trajectory the point reads
     for (long long pt = (long long)blockIdx.x * SONIC_AVG_WARPS + warp; pt < n; pt += nwarps) {
-        const SonicBls b = radii[ia[pt]];
+        const long long u = umap ? umap[pt] : pt;
+        const SonicBls b = radii[ia[u]];
         const double a2 = b.a * b.a;
         const double q0 = Q[pt];
-        const double* ovp = nov ? ov + (size_t)pt * 2 * nov : nullptr;
-        const bool bad = (status[pt] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
-                                        SONIC_ST_TOLSF)) != 0;
-        const double* z = zbuf + pt * SONIC_NPC;
+        const double* ovp = nov ? ov + (size_t)u * 2 * nov : nullptr;
+        const bool bad = (status[u] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
+                                       SONIC_ST_TOLSF)) != 0;
+        const double* z = zbuf + u * SONIC_NPC;
         double* cm = cm_s[warp];
         for (int k = lane; k < SONIC_NPC; k += 32) cm[k] = sonic_capacitance(a2, b.Delta, b.Cm0, z[k]);
         __syncwarp();
@@ -462,7 +465,11 @@ struct SonicPlan {
     int nov = 0;               // charge overtones per point
     int nvar = 0;              // tables per point: 1 + 2 nov + nrates
     double* d_ov = nullptr;
-    long long n = 0;
+    long long n = 0;           // points integrated (unique trajectories)
+    long long n_out = 0;       // points of the output tables (>= n: +Q / -Q pairs share a trajectory)
+    int* d_umap = nullptr;     // [n_out] -> trajectory index, or null (identity)
+    double* d_Qout = nullptr;  // [n_out] signed charges of the output points
+    std::vector<int> umap;
     long long slots = 0;
     int grid = 0, lanes_per_warp = 32;
     size_t zbuf_count = 0, ngbuf_count = 0;
@@ -495,7 +502,7 @@ static int plan_free(SonicPlan* p) {
     cudaFree(p->d_radii); cudaFree(p->d_order); cudaFree(p->d_ia); cudaFree(p->d_ncycles);
     cudaFree(p->d_f); cudaFree(p->d_A); cudaFree(p->d_Q); cudaFree(p->d_fs); cudaFree(p->d_z0);
     pool_give(p->device, 0, p->d_zbuf, p->zbuf_count); pool_give(p->device, 1, p->d_ngbuf, p->ngbuf_count);
-    cudaFree(p->d_tpoint); cudaFree(p->d_out); cudaFree(p->d_ov);
+    cudaFree(p->d_tpoint); cudaFree(p->d_out); cudaFree(p->d_ov); cudaFree(p->d_umap); cudaFree(p->d_Qout);
     cudaFree(p->d_status); cudaFree(p->d_nfe); cudaFree(p->d_nje); cudaFree(p->d_nsteps);
     cudaFree(p->d_counter); cudaFree(p->d_warp_first); cudaFree(p->d_warp_cap); cudaFree(p->d_block_smid);
     for (auto& e : p->ev)
@@ -508,7 +515,8 @@ static int plan_free(SonicPlan* p) {
 template <int NID>
 static void launch_average(SonicPlan* p, int blocks) {
     sonic_average_kernel<NID><<<blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(
-        p->d_zbuf, p->d_ia, p->d_Q, p->d_radii, p->d_status, p->n, p->d_fs, p->nfs, p->nov, p->d_ov, p->d_out);
+        p->d_zbuf, p->d_ia, p->d_Qout, p->d_radii, p->d_status, p->n_out, p->d_fs, p->nfs, p->nov, p->d_ov, p->d_umap,
+        p->d_out);
 }
 
 template <int NID>
@@ -517,6 +525,36 @@ static void launch_rates(const double* vm, long long n, double* out, bool mean) 
         sonic_mean_rates_kernel<NID><<<1, 256>>>(vm, n, out);
     else
         sonic_rates_kernel<NID><<<(int)std::min<long long>((n + 255) / 256, 4096), 256>>>(vm, n, out);
+}
+
+// Per-trajectory array on the device -> per-output-point array on the host.
+template <typename T>
+static int fetch_expanded(SonicPlan* p, const T* d_src, T* out) {
+    if (p->umap.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(out, d_src, (size_t)p->n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return SONIC_OK;
+    }
+    std::vector<T> tmp((size_t)p->n);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_src, (size_t)p->n * sizeof(T), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (long long i = 0; i < p->n_out; i++) out[i] = tmp[p->umap[i]];
+    return SONIC_OK;
+}
+
+// Per-trajectory rows [n][1000] on the device -> per-output-point rows on the host.
+static int fetch_rows_expanded(SonicPlan* p, const double* d_src, double* out) {
+    if (p->umap.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(out, d_src, (size_t)p->n * SONIC_NPC * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return SONIC_OK;
+    }
+    std::vector<double> tmp((size_t)p->n * SONIC_NPC);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), d_src, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    for (long long i = 0; i < p->n_out; i++)
+        memcpy(out + (size_t)i * SONIC_NPC, tmp.data() + (size_t)p->umap[i] * SONIC_NPC, SONIC_NPC * sizeof(double));
+    return SONIC_OK;
 }
 
 extern "C" {
@@ -606,10 +644,13 @@ int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuro
     return sonic_plan_create_ex(device, radii, na, neuron_id, n, ia, f, A, Q, 0, nullptr, fs, nfs, out_plan);
 }
 
-int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
-                         const int32_t* ia, const double* f, const double* A, const double* Q,
+int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n_in,
+                         const int32_t* ia_in, const double* f_in, const double* A_in, const double* Q_in,
                          int novertones, const double* overtones, const double* fs, int nfs,
                          SonicPlan** out_plan) {
+    int64_t n = n_in;
+    const int32_t* ia = ia_in;
+    const double *f = f_in, *A = A_in, *Q = Q_in;
     int rc = check_device(device);
     if (rc) return rc;
     if (neuron_id < 0 || neuron_id >= SONIC_N_NEURONS)
@@ -635,7 +676,61 @@ int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int ne
     CUDA_TRY(cudaMemcpyToSymbol(c_tables, &g_host_tables, sizeof(SonicTables)));
 
     const auto t0 = std::chrono::steady_clock::now();
+    // The mechanics see the charge through Q^2 only (bls.py:482-491): points that differ by the
+    // sign of Q share one trajectory bit for bit (the reference integrates both).  Integrate each
+    // (radius, f, A, |Q|) once; the averaging kernel then applies each point's own signed charge.
+    std::vector<int32_t> u_ia;
+    std::vector<double> u_f, u_A, u_Q;
+    std::vector<int> umap;
+    // |Q| as the integrator sees it: rounded to 36 significant bits (1.5e-11 relative, four orders
+    // below the integrator's tolerance), so that grid values such as the -3 and +3 nC/cm2 of an
+    // np.arange, which differ in their last bits, select the same trajectory -- and so that a point
+    // gets the same trajectory whether it is computed alone, inside a grid, or with zero-amplitude
+    // charge overtones.  The averaging kernel uses the exact charges.
+    auto qint = [](double q) {
+        uint64_t u;
+        q = fabs(q);
+        memcpy(&u, &q, 8);
+        u = (u + 0x8000ULL) & ~0xFFFFULL;
+        memcpy(&q, &u, 8);
+        return q;
+    };
+    if (novertones > 0) {
+        u_Q.resize(n_in);
+        for (int64_t i = 0; i < n_in; i++) u_Q[i] = copysign(qint(Q_in[i]), Q_in[i]);
+        Q = u_Q.data();
+    } else {
+        struct Key {
+            int32_t ia; uint64_t f, A, q;
+            bool operator==(const Key& o) const { return ia == o.ia && f == o.f && A == o.A && q == o.q; }
+        };
+        struct KeyHash {
+            size_t operator()(const Key& k) const {
+                uint64_t h = 1469598103934665603ULL;
+                for (uint64_t v : {(uint64_t)k.ia, k.f, k.A, k.q}) { h ^= v; h *= 1099511628211ULL; h ^= h >> 29; }
+                return (size_t)h;
+            }
+        };
+        auto bits = [](double x) { uint64_t u; memcpy(&u, &x, 8); return u; };
+        std::unordered_map<Key, int, KeyHash> seen;
+        seen.reserve((size_t)n_in * 2);
+        umap.resize(n_in);
+        for (int64_t i = 0; i < n_in; i++) {
+            const double qi = qint(Q_in[i]);
+            const Key k{ia_in[i], bits(f_in[i]), bits(A_in[i]), bits(qi)};
+            auto it = seen.find(k);
+            if (it == seen.end()) {
+                it = seen.emplace(k, (int)u_ia.size()).first;
+                u_ia.push_back(ia_in[i]); u_f.push_back(f_in[i]); u_A.push_back(A_in[i]); u_Q.push_back(qi);
+            }
+            umap[i] = it->second;
+        }
+        n = (int64_t)u_ia.size();
+        ia = u_ia.data(); f = u_f.data(); A = u_A.data(); Q = u_Q.data();
+        if (n == n_in) umap.clear();      // nothing to share: identity (the order is unchanged)
+    }
     SonicPlan* p = new SonicPlan();
+    p->n_out = n_in;
     p->device = device;
     p->neuron_id = neuron_id;
     p->nrates = SONIC_NEURON_NRATES[neuron_id];
@@ -702,7 +797,14 @@ int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int ne
     TRYA(pool_take(device, 0, p->zbuf_count, &p->d_zbuf));
     TRYA(pool_take(device, 1, p->ngbuf_count, &p->d_ngbuf));
     TRYA(dalloc(&p->d_tpoint, n));
-    TRYA(dalloc(&p->d_out, (size_t)p->nvar * n * nfs));
+    TRYA(dalloc(&p->d_out, (size_t)p->nvar * n_in * nfs));
+    TRYA(dalloc(&p->d_Qout, n_in));
+    TRYA(cudaMemcpyAsync(p->d_Qout, Q_in, n_in * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (!umap.empty()) {
+        TRYA(dalloc(&p->d_umap, n_in));
+        TRYA(cudaMemcpyAsync(p->d_umap, umap.data(), n_in * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        p->umap = umap;
+    }
     TRYA(dalloc(&p->d_ov, (size_t)n * 2 * std::max(novertones, 1)));
     if (novertones > 0)
         TRYA(cudaMemcpyAsync(p->d_ov, overtones, (size_t)n * 2 * novertones * sizeof(double), cudaMemcpyHostToDevice, p->stream));
@@ -855,7 +957,7 @@ int sonic_plan_launch(SonicPlan* p) {
     sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(p->ev[2], p->stream));
     {
-        long long blocks = (p->n + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
+        long long blocks = (p->n_out + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
         if (blocks > 148LL * 64) blocks = 148LL * 64;
 #define CALL(ID) launch_average<ID>(p, (int)blocks)
         SONIC_DISPATCH_NEURON(p->neuron_id, CALL)
@@ -889,18 +991,15 @@ int sonic_plan_fetch(SonicPlan* p, double* out_tables, int32_t* out_ncycles, uin
                      double* out_tpoint, uint32_t* out_nrhs) {
     if (!p || !p->launched) return set_err(SONIC_E_ARG, "plan not launched");
     CUDA_TRY(cudaSetDevice(p->device));
-    const size_t n = p->n;
+    int rc = SONIC_OK;
     if (out_tables)
-        CUDA_TRY(cudaMemcpyAsync(out_tables, p->d_out, (size_t)p->nvar * n * p->nfs * sizeof(double),
+        CUDA_TRY(cudaMemcpyAsync(out_tables, p->d_out, (size_t)p->nvar * p->n_out * p->nfs * sizeof(double),
                                  cudaMemcpyDeviceToHost, p->stream));
-    if (out_ncycles)
-        CUDA_TRY(cudaMemcpyAsync(out_ncycles, p->d_ncycles, n * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    if (out_status)
-        CUDA_TRY(cudaMemcpyAsync(out_status, p->d_status, n * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
-    if (out_tpoint)
-        CUDA_TRY(cudaMemcpyAsync(out_tpoint, p->d_tpoint, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    if (out_nrhs)
-        CUDA_TRY(cudaMemcpyAsync(out_nrhs, p->d_nfe, n * sizeof(unsigned), cudaMemcpyDeviceToHost, p->stream));
+    if (out_ncycles && !rc) rc = fetch_expanded(p, p->d_ncycles, out_ncycles);
+    if (out_status && !rc) rc = fetch_expanded(p, p->d_status, out_status);
+    if (out_tpoint && !rc) rc = fetch_expanded(p, p->d_tpoint, out_tpoint);
+    if (out_nrhs && !rc) rc = fetch_expanded(p, p->d_nfe, out_nrhs);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     return SONIC_OK;
 }
@@ -908,10 +1007,7 @@ int sonic_plan_fetch(SonicPlan* p, double* out_tables, int32_t* out_ncycles, uin
 int sonic_plan_fetch_zprofiles(SonicPlan* p, double* out_z) {
     if (!p || !p->launched || !out_z) return set_err(SONIC_E_ARG, "plan not launched or null buffer");
     CUDA_TRY(cudaSetDevice(p->device));
-    CUDA_TRY(cudaMemcpyAsync(out_z, p->d_zbuf, (size_t)p->n * SONIC_NPC * sizeof(double),
-                             cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    return SONIC_OK;
+    return fetch_rows_expanded(p, p->d_zbuf, out_z);
 }
 
 int sonic_plan_fetch_relcm(SonicPlan* p, double* out_cm) {
@@ -922,11 +1018,11 @@ int sonic_plan_fetch_relcm(SonicPlan* p, double* out_cm) {
     CUDA_TRY(dalloc(&d_cm, total));
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     sonic_relcm_kernel<<<blocks, 256, 0, p->stream>>>(p->d_zbuf, p->d_ia, p->d_radii, p->n, d_cm);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_cm, d_cm, total * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    int rc = SONIC_OK;
+    if (cudaGetLastError() != cudaSuccess) rc = set_err(SONIC_E_CUDA, "relative capacitance kernel failed");
+    if (!rc) rc = fetch_rows_expanded(p, d_cm, out_cm);
     cudaFree(d_cm);
-    if (e != cudaSuccess) return set_err(SONIC_E_CUDA, "relative capacitance fetch failed: %s", cudaGetErrorString(e));
+    if (rc) return rc;
     p->launches += 1;
     return SONIC_OK;
 }
@@ -957,7 +1053,7 @@ int sonic_plan_stats(SonicPlan* p, SonicStats* st) {
         for (int b = 0; b < p->grid; b++) diff += now[b] != p->probe_smid[b];
         fprintf(stderr, "[sonic] block placement: %d of %d blocks differ from the probe\n", diff, p->grid);
     }
-    st->n_points = n;
+    st->n_points = (uint64_t)p->n_out;
     st->n_launches = p->launches;
     st->ms_total = p->ms_upload;
     return SONIC_OK;
