@@ -483,3 +483,19 @@ def test_charge_overtones_lookup_layout(gpu):
     outs = Batch(nbls.computeEffVars, queue)(mpi=True, loglevel=10)
     assert outs[0][0][0]['V'] == lkp['V'][0, 0, 1, 1, 1, 0, 0]
     assert outs[1][0][0]['A_V1'] == lkp['A_V1'][0, 0, 1, 0, 0, 0, 0]
+
+
+def test_multi_device_mask_matches_single_device(gpu):
+    ''' sonic_lookup_run with several bits of device_mask set (one host thread per device, host-side
+        scatter): bit-identical to the single-device result.  Needs >= 2 GPUs in the process. '''
+    if gpu.device_count() < 2:
+        pytest.skip('single-GPU box')
+    ps = _ps()
+    g = load_grid('c1_RS_32nm_500kHz.npz')
+    pn = ps.getPointNeuron('RS')
+    one = ps.computeAStimLookup(pn, g['a'], g['f'], g['A'], g['fs'], g['Q'], loglevel=10)
+    many, info = ps.computeAStimLookup(pn, g['a'], g['f'], g['A'], g['fs'], g['Q'], mpi=True, loglevel=10,
+                                       return_info=True)
+    for k in ['V'] + pn.rates:
+        np.testing.assert_array_equal(one[k], many[k])
+    assert info['stats']['n_points'] == 1000
