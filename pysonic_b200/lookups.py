@@ -5,7 +5,6 @@
 import os
 import pickle
 
-import numpy as np
 
 
 class Lookup:

@@ -18,7 +18,7 @@ import pytest
 
 import sonic_oracle as so
 from conftest import load_grid
-from parity import ATOL, RTOL, assert_grid_parity, grid_err, rel_err, summarize
+from parity import RTOL, assert_grid_parity, grid_err, rel_err
 
 pytestmark = pytest.mark.gpu
 

@@ -1,6 +1,5 @@
 # -*- coding: utf-8 -*-
 ''' Development check on a GPU box: FP64 peak, smoke, C1 parity against the golden grid, C2 timing. '''
-import json
 import os
 import sys
 import time

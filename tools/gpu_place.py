@@ -1,5 +1,4 @@
 import os, sys, time
-import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 sys.path.insert(0, ROOT)
 import bench, pysonic_b200 as ps
