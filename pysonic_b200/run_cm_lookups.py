@@ -11,6 +11,7 @@ import numpy as np
 
 from .bls import BilayerSonophore
 from .lookups import Lookup
+from .run_lookups import _validate
 
 logger = logging.getLogger('pysonic_b200')
 
@@ -18,19 +19,8 @@ logger = logging.getLogger('pysonic_b200')
 def computeCmLookup(bls, fref, Aref, mpi=False, loglevel=logging.INFO):
     ''' Drop-in for `computeCmLookup` of scripts/run_Cm_lookups.py:19: refs `f, A, t`, one table
         `Cm_rel` of shape (nf, nA, 1000). '''
-    descs = {'f': 'US frequencies', 'A': 'US amplitudes'}
     refs = {'f': fref, 'A': Aref}
-    for key, values in refs.items():
-        if not isinstance(values, (list, tuple, np.ndarray)):
-            raise TypeError(f'Invalid {descs[key]} (must be provided as list or numpy array)')
-        if not all(isinstance(x, float) for x in values):
-            raise TypeError(f'Invalid {descs[key]} (must all be float typed)')
-        if len(values) == 0:
-            raise ValueError(f'Empty {key} array')
-        if key == 'f' and min(values) <= 0:
-            raise ValueError(f'Invalid {descs[key]} (must all be strictly positive)')
-        if key == 'A' and min(values) < 0:
-            raise ValueError(f'Invalid {descs[key]} (must all be positive or null)')
+    _validate(refs)        # same checks and exception types as for the effective-variable lookups
     refs = {k: np.asarray(v, dtype=np.float64) for k, v in refs.items()}
     dims = [x.size for x in refs.values()]
     logger.log(loglevel, 'Starting Cm simulation batch for %s', bls)
