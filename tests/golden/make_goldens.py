@@ -250,6 +250,16 @@ def gen_c2sub(amp_scale=1.0, tag=''):
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
 
 
+def gen_cortical(amp_scale=1.0, tag=''):
+    ''' Small grids for the other cortical neurons that share the RS kinetics family (FS, LTS, IB):
+        two radii, three frequencies, five amplitudes, six charges. '''
+    Aall = c2_amps()
+    for name in ['FS', 'LTS', 'IB']:
+        Q = default_charges(name)
+        _grid_to_npz(f'c7_{name}_sub{tag}.npz', name, [16e-9, 64e-9], [100e3, 1e6, 3e6],
+                     Aall[[0, 24, 38, 46, 50]], Q[::max(1, Q.size // 5)], [1.0], amp_scale)
+
+
 def _ov_point(args):
     name, a, f, A, Q, fs, ov = args
     _counters['ncycles'] = 0
@@ -311,9 +321,11 @@ def gen_noise():
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
-            'c2sub': gen_c2sub, 'cm': gen_cm, 'overtones': gen_overtones, 'noise': gen_noise,
+            'c2sub': gen_c2sub, 'cm': gen_cm,
+            'cortical': lambda: (gen_cortical(), gen_cortical(1.0 + 4.440892098500626e-16, '_ulp_up'),
+                                 gen_cortical(1.0 - 4.440892098500626e-16, '_ulp_dn')), 'overtones': gen_overtones, 'noise': gen_noise,
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm')):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical')):
             fn()

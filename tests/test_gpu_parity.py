@@ -134,9 +134,10 @@ def test_c2_subsample_parity(gpu):
 
 @pytest.mark.parametrize('fname', ['c3_STN_sub.npz', 'c4_FHnode_sub.npz', 'c4_SWnode_sub.npz',
                                    'c4_MRGnode_sub.npz', 'c4_SUseg_sub.npz', 'c5_RE_sub.npz',
-                                   'c5_TC_sub.npz'])
+                                   'c5_TC_sub.npz', 'c7_FS_sub.npz', 'c7_LTS_sub.npz', 'c7_IB_sub.npz'])
 def test_other_neuron_grids(gpu, fname):
-    ''' C3 (STN with a coverage sweep), C4 (peripheral fibres), C5 (thalamic, high amplitudes). '''
+    ''' C3 (STN with a coverage sweep), C4 (peripheral fibres), C5 (thalamic, high amplitudes), and
+        the other cortical neurons (FS, LTS, IB) at 16 and 64 nm. '''
     g = load_grid(fname)
     up, dn = load_grid(fname.replace('.npz', '_ulp_up.npz')), load_grid(fname.replace('.npz', '_ulp_dn.npz'))
     keys = [str(k) for k in g['keys']]
