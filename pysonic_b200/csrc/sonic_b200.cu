@@ -212,20 +212,25 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
         }
-        if (active) {
-            double fv[3];
-            if (p.nov) sonic_update_charge(p, s.tn);
-            if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-            sonic_tick(s, H, &tab, p, sink, period, fv, wmask);
-            if (s.phase == PH_DONE) {
-                job.ncycles[pt] = s.cyc;
-                job.status[pt] = s.status;
-                job.nfe[pt] = s.nfe;
-                job.nje[pt] = s.nje;
-                job.nsteps[pt] = s.nsteps;
-                job.tpoint[pt] = (double)(sonic_globaltimer() - t_start) * 1e-9;
-                pt = -1;
+        // tick until a lane of this warp finishes its point (the set of busy lanes is fixed till then)
+        bool fin = false;
+        do {
+            if (active) {
+                double fv[3];
+                if (p.nov) sonic_update_charge(p, s.tn);
+                if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
+                sonic_tick(s, H, &tab, p, sink, period, fv, wmask);
+                fin = s.phase == PH_DONE;
             }
+        } while (!__any_sync(0xffffffffu, fin));
+        if (fin) {
+            job.ncycles[pt] = s.cyc;
+            job.status[pt] = s.status;
+            job.nfe[pt] = s.nfe;
+            job.nje[pt] = s.nje;
+            job.nsteps[pt] = s.nsteps;
+            job.tpoint[pt] = (double)(sonic_globaltimer() - t_start) * 1e-9;
+            pt = -1;
         }
     }
 }

@@ -117,6 +117,8 @@ struct SonicTables {
     double c12[5];    // cm1[q] / cm2[q]
     double rtesco[2][12][3];   // 1 / tesco (0 where tesco is 0)
     double rcon[2][12];        // 1 / (tesco[.][q][1] * conit(q)), conit(q) = 0.5 / (q + 2)
+    double c21e[5];            // (cm2[q] / cm1[q])^(1 / (q + 2)): ratio of the two families' error constants,
+    double c12e[5];            // (cm1[q] / cm2[q])^(1 / (q + 2))  raised to the step-size exponent of order q + 1
 };
 
 // Per-radius constants (one entry per sonophore radius of the lookup).
@@ -381,11 +383,18 @@ SONIC_HD double sonic_powr(double d, double ex) {
 #endif
 }
 
-// (d * c)^ex; `lc` = log(c) and `*ld` (a cache for log(d)) are kept for the host build's
-// signature only.
-SONIC_HD double sonic_powr_scaled(double d, double c, double lc, double ex, double* ld) {
-    (void)lc; (void)ld;
-    return sonic_powr(d * c, ex);
+// (d * c)^ex where d^ex may already be at hand (`*pd`, NaN = not yet) and ce = c^ex is tabulated:
+// on the device the power of the local error estimate is computed once per step and shared by
+// every step-size candidate derived from it; the host build takes the power of the product.
+SONIC_HD double sonic_powr_scaled(double d, double c, double ce, double ex, double* pd) {
+#if defined(__CUDA_ARCH__)
+    (void)c;
+    if (*pd != *pd) *pd = sonic_powr(d, ex);
+    return *pd * ce;
+#else
+    (void)ce; (void)pd;
+    return pow(d * c, ex);
+#endif
 }
 
 // Lennard-Jones intermolecular pressure (bls.py:29-41,472-480).
@@ -965,7 +974,7 @@ struct SonicStepCtx {
 SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepCtx* c) {
     if (c->rhsm0 != c->rhsm0) {
         const double exsm = T->rk[s.nq + 1];
-        c->rhsm0 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, 1.0, 0.0, exsm, &c->lds) + 0.0000012);
+        c->rhsm0 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, 1.0, 1.0, exsm, &c->lds) + 0.0000012);
     }
     return c->rhsm0;
 }
@@ -1054,7 +1063,7 @@ SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicT
             rh1 = fmin(rh1, rh1it);
             // nq <= 5 = MXORDS here, so the "reduce to MXORDS" branch cannot be taken
             const double c12 = T->c12[s.nq - 1];
-            rh2 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c12, -T->lc21[s.nq - 1], exsm, &ctx->lds) +
+            rh2 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c12, T->c12e[s.nq - 1], exsm, &ctx->lds) +
                             0.0000012);
             nqm2 = s.nq;
             if (rh2 < 5.0 * rh1) return false;
@@ -1074,7 +1083,7 @@ SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicT
     // currently BDF (nq <= 5 <= MXORDN): consider Adams at the same order
     const double c21 = T->c21[s.nq - 1];
     double dm1 = s.dsm * c21;
-    double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->lc21[s.nq - 1], exsm, &ctx->lds) +
+    double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->c21e[s.nq - 1], exsm, &ctx->lds) +
                            0.0000012);
     const int nqm1 = s.nq;
     const double exm1 = exsm;
@@ -1647,6 +1656,10 @@ static void sonic_fill_tables(SonicTables* T) {
     }
     T->rk[0] = 0.0;
     for (int i = 1; i < 16; i++) T->rk[i] = 1.0 / i;
+    for (int i = 0; i < 5; i++) {
+        T->c21e[i] = pow(T->c21[i], 1.0 / (i + 2));
+        T->c12e[i] = pow(T->c12[i], 1.0 / (i + 2));
+    }
     for (int m = 0; m < 2; m++)
         for (int q = 0; q < 12; q++) {
             for (int k = 0; k < 3; k++) T->rtesco[m][q][k] = T->tesco[m][q][k] != 0.0 ? 1.0 / T->tesco[m][q][k] : 0.0;

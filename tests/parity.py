@@ -72,11 +72,12 @@ def assert_grid_parity(tables, ncycles, golden, up, dn, keys, label=''):
     assert np.all(err[quiet] <= RTOL), msg + f' | quiet-row violations {int(np.sum(err[quiet] > RTOL))}'
     # (2) no worse than the reference's own reproducibility
     # (counted per ODE point -- all coverage fractions of a point share one integration -- and
-    #  never asking for less than one point, the resolution of a two-sample noise estimate)
+    #  with one point of slack: the envelope is a two-sample estimate of the reference's noise and
+    #  the engine is a third draw)
     bad_pts = int(np.sum(err.max(axis=-1) > RTOL))
     env_pts = int(np.sum(env.max(axis=-1) > RTOL))
     npts = err[..., 0].size
-    assert bad_pts <= max(1.5 * env_pts, 0.005 * npts, 1), msg + f' | points > tol: {bad_pts} vs self {env_pts}'
+    assert bad_pts <= max(1.5 * env_pts + 1, 0.005 * npts), msg + f' | points > tol: {bad_pts} vs self {env_pts}'
     assert s_err['median'] <= max(3 * s_env['median'], 2e-6), msg
     # cycle counts: identical wherever the reference's own count is reproducible, and overall
     # agreement not below the reference's self-agreement
