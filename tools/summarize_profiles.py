@@ -81,8 +81,16 @@ def ncu_full(tag):
             fh.write('  warp stall reasons (pc sampling):\n')
             for k, v in sorted(st.items(), key=lambda x: -x[1])[:8]:
                 fh.write(f'    {k.replace("smsp__pcsamp_warps_issue_stalled_", ""):30s} {100 * v / tot:6.1f} %\n')
+    # right-hand sides evaluated by one C1 launch (from the plain run of the same command)
+    nticks = '1'
+    plain = os.path.join(OUT, f'plain_c1_{tag}.log')
+    if os.path.isfile(plain):
+        for ln in open(plain):
+            if ln.startswith('{'):
+                nticks = str(json.loads(ln)['roofline']['rhs_evaluations'])
     sass = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'sass_profile.py'), rep,
-                           os.path.join(ROOT, 'pysonic_b200', 'libsonic_b200.so')], capture_output=True, text=True).stdout
+                           os.path.join(ROOT, 'pysonic_b200', 'libsonic_b200.so'),
+                           '_Z22sonic_integrate_kernel8SonicJob', nticks], capture_output=True, text=True).stdout
     with open(os.path.join(PROF, f'{tag}_sass_profile.txt'), 'w') as fh:
         fh.write('# executed warp-instructions per source function of sonic_integrate_kernel (ncu source page x nvdisasm line info)\n')
         fh.write('\n'.join(sass.splitlines()[:45]) + '\n')
