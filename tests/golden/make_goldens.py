@@ -10,6 +10,7 @@
         python tests/golden/make_goldens.py neurons     # small grids for the C3-C5 neurons
         python tests/golden/make_goldens.py c2sub       # stratified subsample of RS-4D (C2)
         python tests/golden/make_goldens.py noise       # reference re-run with +-2 ulp amplitude
+        python tests/golden/make_goldens.py noise4      # small grids re-run with +-4 ulp amplitude
         python tests/golden/make_goldens.py all
 
     Every record is produced by `NeuronalBilayerSonophore.computeEffVars`
@@ -322,10 +323,13 @@ if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
             'c2sub': gen_c2sub, 'cm': gen_cm,
+            'noise4': lambda: [fn(sc, tg) for fn in (gen_neurons, gen_cortical)
+                               for sc, tg in ((1.0 + 8.881784197001252e-16, '_ulp_up2'),
+                                              (1.0 - 8.881784197001252e-16, '_ulp_dn2'))],
             'cortical': lambda: (gen_cortical(), gen_cortical(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                  gen_cortical(1.0 - 4.440892098500626e-16, '_ulp_dn')), 'overtones': gen_overtones, 'noise': gen_noise,
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical')):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4')):
             fn()

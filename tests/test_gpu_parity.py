@@ -140,10 +140,12 @@ def test_other_neuron_grids(gpu, fname):
         the other cortical neurons (FS, LTS, IB) at 16 and 64 nm. '''
     g = load_grid(fname)
     up, dn = load_grid(fname.replace('.npz', '_ulp_up.npz')), load_grid(fname.replace('.npz', '_ulp_dn.npz'))
+    more = [load_grid(fname.replace('.npz', t)) for t in ('_ulp_up2.npz', '_ulp_dn2.npz')
+            if os.path.isfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', fname.replace('.npz', t)))]
     keys = [str(k) for k in g['keys']]
     lkp, info = _lookup(g)
     assert list(lkp.tables.keys()) == keys + ['tcomp']
-    assert_grid_parity(lkp.tables, info['ncycles'], g, up, dn, keys, fname)
+    assert_grid_parity(lkp.tables, info['ncycles'], g, up, dn, keys, fname, more=more)
 
 
 def test_seeded_points_against_oracle(gpu):
