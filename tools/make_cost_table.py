@@ -19,9 +19,10 @@ import numpy as np
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 
-A_EDGES_KPA = [0., 0.05, 0.3, 0.7, 1.5, 3., 5., 8., 12., 20., 35., 60., 100., 170., 280., 450., 1e9]
-Q_EDGES = [0., 10., 20., 30., 40., 50., 60., 70., 80., 88., 95., 101., 110., 125., 140., 160., 180., 200.,
-           225., 250., 275., 1e9]   # |Q| in nC/cm2
+A_EDGES_KPA = [0., 0.05, 0.3, 0.7, 1.5, 3., 5., 8., 12., 20., 35., 60., 100., 140., 190., 250., 320., 400., 500.,
+               1e9]
+Q_EDGES = [0., 10., 20., 30., 40., 50., 60., 70., 80., 85., 89., 92., 95., 98., 101., 104., 110., 125., 140.,
+           160., 180., 200., 225., 250., 275., 1e9]   # |Q| in nC/cm2
 
 
 def main():
