@@ -504,3 +504,21 @@ def test_multi_device_mask_matches_single_device(gpu):
     for k in ['V'] + pn.rates:
         np.testing.assert_array_equal(one[k], many[k])
     assert info['stats']['n_points'] == 1000
+
+
+def test_embedding_depth_against_oracle(gpu):
+    ''' Sonophore embedded in tissue (kA_tissue = 2 alpha f d, bls.py:583-602): engine vs the oracle
+        run live, and a visibly different answer from the free sonophore. '''
+    ps = _ps()
+    pn = ps.getPointNeuron('RS')
+    f, A, Q, d = 500e3, 200e3, -71.9e-5, 2e-6
+    nbls = ps.NeuronalBilayerSonophore(32e-9, pn, embedding_depth=d)
+    free = ps.NeuronalBilayerSonophore(32e-9, pn)
+    ev, _ = nbls.computeEffVars(ps.AcousticDrive(f, A), 1.0, Q)
+    ev_free, _ = free.computeEffVars(ps.AcousticDrive(f, A), 1.0, Q)
+    b = so.get_bls('RS', 32e-9)
+    b.d = d
+    ref, ncyc = so.compute_effvars('RS', b, f, A, 1.0, Q)
+    for k in ref[0]:
+        assert rel_err(ev[0][k], ref[0][k]) <= RTOL, (k, ev[0][k], ref[0][k])
+    assert abs(ev[0]['V'] - ev_free[0]['V']) > 1e-3 * abs(ev_free[0]['V'])
