@@ -627,7 +627,7 @@ struct SonicLane {
     double pdest, pdlast, pdnorm, dsm, pnorm, del, delp, rate;
     double yj_save, jac_r0;
     int nq, meth, miter, mused, ialth, ipup, icount, irflag, jcur, kflag, m, ncf;
-    int nst, nslp, nslast, jstart, tab_meth, jcol, ierpj, ipvt;
+    int nst, nslp, nslast, jstart, tab_meth, ierpj, ipvt;
     int phase;
     // ---- output / cycle bookkeeping ----
     double t0, tstop, tstep, tout;
