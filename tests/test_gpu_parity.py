@@ -522,3 +522,23 @@ def test_embedding_depth_against_oracle(gpu):
     for k in ref[0]:
         assert rel_err(ev[0][k], ref[0][k]) <= RTOL, (k, ev[0][k], ref[0][k])
     assert abs(ev[0]['V'] - ev_free[0]['V']) > 1e-3 * abs(ev_free[0]['V'])
+
+
+def test_robustness_outside_the_baseline_grids(gpu):
+    ''' Random points far outside the BASELINE grids (f 10 kHz - 10 MHz, A up to 2 MPa, |Q| up to
+        300 nC/cm2): the call returns, every point has finite tables or a failure status with NaNs
+        (the reference's odeint would print "excess work" and hand back garbage there). '''
+    ps = _ps()
+    rng = np.random.default_rng(1)
+    n = 48
+    for name, a in (('RS', 16e-9), ('SWnode', 32e-9)):
+        nbls = ps.NeuronalBilayerSonophore(a, ps.getPointNeuron(name))
+        f = 10 ** rng.uniform(4.3, 7, n)
+        A = np.where(rng.random(n) < 0.1, 0., 10 ** rng.uniform(2, np.log10(2e6), n))
+        Q = rng.uniform(-300e-5, 300e-5, n)
+        out, ncyc, status, tp, nrhs, st = nbls.effvars_batch(f, A, Q, [0.5, 1.0])
+        ok = (status & ~np.uint32(3)) == 0
+        assert ok.sum() >= n // 2
+        assert np.isfinite(out[:, ok]).all()
+        assert np.isnan(out[:, ~ok]).all()
+        assert np.all((ncyc[ok] >= 2) & (ncyc[ok] <= 11))
