@@ -42,6 +42,7 @@ extern "C" {
 #endif
 
 #define SONIC_ABI_VERSION 1
+#define SONIC_ABI_MAX_OVERTONES 4   /* charge overtones per point accepted by the *_ex entry points */
 
 #define SONIC_OK 0
 #define SONIC_E_NODEVICE (-1)   /* no CUDA device / bad device index */
@@ -75,7 +76,8 @@ typedef struct {
 typedef struct {
     uint64_t n_points;      /* output points; the counters below cover the trajectories actually
                              * integrated (points that differ by the sign of Q share one) */
-    uint64_t n_rhs;         /* right-hand-side evaluations (integrator ticks) */
+    uint64_t n_rhs;         /* right-hand-side evaluations counted as LSODA counts them (3 per
+                             * Jacobian); the kernel evaluates n_rhs - 2 n_jac full right-hand sides */
     uint64_t n_jac;         /* finite-difference Jacobian evaluations */
     uint64_t n_steps;       /* accepted integrator steps */
     uint64_t n_cycles;      /* acoustic cycles simulated */
