@@ -25,8 +25,14 @@
     over the bounded sample; rank 0 only.
 
     Under torchrun (N > 1) every rank drives its own GPU; there is no data-path collective.
-    --scaling weak (default): every rank regenerates one full RS 4-D table (N tables per step);
-    --scaling strong: the single table is sharded over the ranks by cost-sorted round-robin.
+    --scaling strong (default): ONE RS 4-D table sharded over the ranks (whole trajectory groups dealt
+    round-robin in cost order, `computeAStimLookup(mpi=True)` for the end-to-end figure, one final
+    all_gather); the replica figure (every rank regenerates a full table) is reported next to it as
+    `config.weak`.  --scaling weak makes the replica figure the headline instead.
+
+    Extra keys of the own arm: `parity` (the literal north_star figures of this build, computed live
+    against the reference-generated fixtures under tests/golden), `multi_neuron` (the four cortical
+    tables through one integrator launch, N = 1).
 '''
 
 import argparse
@@ -157,7 +163,7 @@ def reference_arm(args):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
-        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
+        'higher_is_better': True, 'scaling': args.scaling or 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic (deterministic grid from the reference formulas)',
         'config': {'workload': w['label'], 'sample': desc},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
@@ -213,11 +219,43 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None):
+    ''' The literal north_star figures of this build against the reference-generated fixtures
+        (tests/golden, made by tests/golden/make_goldens.py from the unmodified reference): BASELINE
+        config 1 in full, and -- when the full RS 4-D table is at hand -- its 10 710 nodes of the dense
+        C2 fixture. '''
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from parity import parity_stats
+    gold = os.path.join(ROOT, 'tests', 'golden')
+    out = {'tolerance': 'V and rates within 1e-4 relative (1e-9 absolute); per-entry bound max(1e-4, 5 x the '
+                        "entry's own deviation under +-2 ulp re-runs of the reference)"}
+
+    def variants(stem):
+        return [np.load(os.path.join(gold, stem + t)) for t in ('_ulp_up.npz', '_ulp_dn.npz')
+                if os.path.isfile(os.path.join(gold, stem + t))]
+
+    g = np.load(os.path.join(gold, 'c1_RS_32nm_500kHz.npz'))
+    keys = [str(k) for k in g['keys']]
+    lkp, info = ps.computeAStimLookup(ps.getPointNeuron('RS'), g['a'], g['f'], g['A'], g['fs'], g['Q'],
+                                      return_info=True, loglevel=10)
+    out['c1_full_1000_points'] = parity_stats(lkp.tables, info['ncycles'], g, variants('c1_RS_32nm_500kHz'), keys)
+    big = os.path.join(gold, 'c2_RS_big.npz')
+    if lkp_c2 is not None and os.path.isfile(big) and len(variants('c2_RS_big')) == 2:
+        g = np.load(big)
+        iQ = [int(np.argmin(np.abs(w_c2['Q'] - x))) for x in g['Q']]
+        if np.array_equal(w_c2['Q'][iQ], g['Q']) and np.array_equal(w_c2['A'], g['A']):
+            sub = {k: lkp_c2[k][:, :, :, iQ] for k in keys}
+            out['c2_dense_10710_points'] = parity_stats(sub, info_c2['ncycles'][:, :, :, iQ], g,
+                                                        variants('c2_RS_big'), keys)
+    return out
+
+
 def gpu_arm(args):
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     w = workload(args.workload)
+    scaling = args.scaling or 'strong'
 
     # the CPU baseline leg runs first, before any CUDA context exists in this process (fork)
     cpu = None
@@ -232,7 +270,7 @@ def gpu_arm(args):
     import torch.distributed as dist
     import pysonic_b200 as ps
     from pysonic_b200 import _lib
-    from pysonic_b200.parallel import predicted_log_cost, shard_indices
+    from pysonic_b200.parallel import predicted_log_cost, shard_indices, trajectory_groups
 
     _lib.load()
     if _lib.device_count() < 1:
@@ -254,54 +292,56 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     pn = ps.getPointNeuron(w['neuron'])
     nrates = len(pn.rates)
     bls = [ps.NeuronalBilayerSonophore(float(a), pn).abi_params() for a in w['a']]
-    ia, f, A, Q = flatten(w)
-    n_grid = ia.size
-    if args.scaling == 'strong' and world > 1:
-        idx = shard_indices(predicted_log_cost(w['a'][ia], f, A, Q), rank, world)
-        ia, f, A, Q = ia[idx], f[idx], A[idx], Q[idx]
-    n_local = ia.size
-    n_job = n_grid * world if args.scaling == 'weak' else n_grid
-
+    ia_all, f_all, A_all, Q_all = flatten(w)
+    n_grid = ia_all.size
     peak = _lib.fp64_peak(local_rank)          # FP64 FMA peak of this device, TFLOP/s
-
-    # ---- resident plan on a torch stream (so that torch events see the launches) ----
     stream = torch.cuda.Stream(device=dev)
-    plan = _lib.Plan(local_rank, bls, pn.neuron_id, nrates, ia, f, A, Q, w['fs'])
-    plan.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
-    def step():
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
-        plan.launch()
+    def measure(mode, steps, warmup):
+        ''' Resident plan of this rank's share of the work (the whole grid, or its shard of it) on a
+            torch stream; W + K launches, CUDA events around the K timed ones, max over ranks. '''
+        ia, f, A, Q = ia_all, f_all, A_all, Q_all
+        if mode == 'strong' and world > 1:
+            idx = shard_indices(predicted_log_cost(w['a'][ia], f, A, Q), rank, world,
+                                trajectory_groups(ia, f, A, Q))
+            ia, f, A, Q = ia[idx], f[idx], A[idx], Q[idx]
+        plan = _lib.Plan(local_rank, bls, pn.neuron_id, nrates, ia, f, A, Q, w['fs'])
+        plan.set_stream(stream.cuda_stream)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    clocks = Clocks(local_rank)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record(stream)
-    ms_int = 0.0
-    for _ in range(args.steps):
-        step()
-    ev[1].record(stream)
-    barrier()
-    clk = clocks.stop()
-    ms_region = max_over_ranks(ev[0].elapsed_time(ev[1]))
-    st = plan.stats()                              # counters + per-kernel event times of the last launch
+        def step():
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+            plan.launch()
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        clocks = Clocks(local_rank)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(stream)
+        for _ in range(steps):
+            step()
+        ev[1].record(stream)
+        barrier()
+        clk = clocks.stop()
+        ms_region = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        st = plan.stats()                      # counters + per-kernel event times of the last launch
+        plan.destroy()
+        n_job = n_grid * world if (mode == 'weak' and world > 1) else n_grid
+        return {'ms_per_step': ms_region / steps, 'value': n_job / (ms_region / steps * 1e-3), 'stats': st,
+                'clocks': clk, 'n_job': n_job, 'n_local': ia.size}
+
+    head = measure(scaling, args.steps, args.warmup)
+    other = None
+    if world > 1:
+        other = measure('weak' if scaling == 'strong' else 'strong', max(1, args.steps - 1), 1)
+    st = head['stats']
     ms_int = st['ms_integrate']
-    ms_per_step = ms_region / args.steps
-    value = n_job / (ms_per_step * 1e-3)
+    n_job, n_local = head['n_job'], head['n_local']
 
     # ---- roofline of the dominant kernel (the integrator), this rank ----
     n_corr = st['n_rhs'] - 3 * st['n_jac'] - st['n_cycles']
@@ -336,48 +376,79 @@ def gpu_arm(args):
     d2h = n_local * ((1 + nrates) * w['fs'].size * 8 + 4 + 4 + 8)
 
     def e2e_step():
-        if args.scaling == 'strong' and world > 1:
+        if scaling == 'strong' and world > 1:
             return ps.computeAStimLookup(pn, w['a'], w['f'], w['A'], w['fs'], w['Q'], mpi=True,
-                                         loglevel=10)
+                                         loglevel=10, return_info=True)
         return ps.computeAStimLookup(pn, w['a'], w['f'], w['A'], w['fs'], w['Q'], loglevel=10,
-                                     device=local_rank, shard=False)
+                                     device=local_rank, shard=False, return_info=True)
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        lkp = e2e_step()
+        lkp, info = e2e_step()
     torch.cuda.synchronize()
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_job * args.steps / dt_e2e
     finite = all(np.isfinite(v).all() for v in lkp.tables.values())
 
-    plan.destroy()
+    # ---- extras (rank 0, outside every timed region) ----
+    parity = multi = None
+    if rank == 0 and not args.no_extras:
+        parity = live_parity(ps, lkp if args.workload == 'c2' else None, info, w)
+    if world == 1 and not args.no_extras and args.workload == 'c2':
+        names = ['RS', 'FS', 'LTS', 'IB']
+        pns = [ps.getPointNeuron(x) for x in names]
+        Qs = [np.arange(p_.Qbounds[0], p_.Qbounds[1] + 1e-5, 1e-5) for p_ in pns]
+        ps.computeAStimLookups(pns, w['a'], w['f'], w['A'], w['fs'], Qs, loglevel=10, device=local_rank)
+        t0 = time.perf_counter()
+        lk4, i4 = ps.computeAStimLookups(pns, w['a'], w['f'], w['A'], w['fs'], Qs, loglevel=10,
+                                         device=local_rank, return_info=True)
+        dt4 = time.perf_counter() - t0
+        npts = sum(int(np.prod(x['V'].shape)) for x in lk4)
+        same = all(np.array_equal(lk4[0][k], lkp[k]) for k in ['V'] + pn.rates)
+        multi = {'neurons': names, 'grid_points': npts, 'seconds_e2e': dt4, 'points_per_s_e2e': npts / dt4,
+                 'kernel_ms_integrate': i4['stats']['ms_integrate'],
+                 'time_vs_one_table': dt4 / (dt_e2e / args.steps),
+                 'rs_table_bit_identical_to_single_neuron_run': bool(same),
+                 'api': 'pysonic_b200.computeAStimLookups -> sonic_lookup_run_multi (one integrator launch, '
+                        'one averaging launch per neuron)'}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    par = {'weak': f'{world} ranks, one full table per rank (replicas), no collective',
+           'strong': f'{world} ranks, ONE table sharded (trajectory groups dealt round-robin in cost order), '
+                     'no data-path collective, one final all_gather of the tables'}
+    config = {
+        'workload': w['label'], 'ode_points_per_step': n_job, 'grid_points_per_step': n_job * w['fs'].size,
+        'parallelism': '1 GPU' if world == 1 else par[scaling],
+        'l2': 'explicit 256 MB flush write before every step (and 1.35 GB of cycle profiles per step)',
+    }
+    if other is not None:
+        config['weak' if scaling == 'strong' else 'strong'] = {
+            'value': other['value'], 'unit': UNIT, 'ms_per_step': other['ms_per_step'],
+            'parallelism': par['weak' if scaling == 'strong' else 'strong']}
     line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
+        'metric': METRIC, 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': head['ms_per_step'], 'higher_is_better': True,
+        'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic (deterministic grid from the reference formulas, no RNG)',
-        'config': {
-            'workload': w['label'], 'ode_points_per_step': n_job, 'grid_points_per_step': n_job * w['fs'].size,
-            'parallelism': ('1 GPU' if world == 1 else
-                            f'{world} ranks, one full table per rank, no collective' if args.scaling == 'weak'
-                            else f'{world} ranks, one table sharded by cost-sorted round-robin, host gather'),
-            'l2': 'explicit 256 MB flush write before every step (and 1.35 GB of cycle profiles per step)',
-        },
+        'config': config,
         'roofline': roofline,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': dt_e2e / args.steps * 1e3, 'api': 'pysonic_b200.computeAStimLookup -> '
-                'sonic_lookup_run (C ABI, host buffers)', 'tables_finite': bool(finite)},
-        'gpu_launches': 3 * args.steps,
+                'sonic_lookup_run / sonic_points_run (C ABI, host buffers)', 'tables_finite': bool(finite)},
+        'gpu_launches': 4 * args.steps,
         'kernel_ms': {'z0': st['ms_z0'], 'integrate': st['ms_integrate'], 'average': st['ms_average']},
-        'clocks': clk,
+        'clocks': head['clocks'],
     }
+    if parity is not None:
+        line['parity'] = parity
+    if multi is not None:
+        line['multi_neuron'] = multi
     if cpu is not None:
         line['cpu_baseline'] = cpu
     print(json.dumps(line), flush=True)
@@ -390,7 +461,9 @@ def main():
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='own', choices=['own', 'reference'])
     p.add_argument('--workload', default='c2', choices=['c1', 'c2'])
-    p.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    p.add_argument('--scaling', default=None, choices=['weak', 'strong'],
+                   help='N > 1: strong (default) = one table sharded over the ranks, weak = one table per rank')
+    p.add_argument('--no-extras', action='store_true', help='skip the parity and multi-neuron legs')
     p.add_argument('--cpu-budget', type=float, default=20.0, help='seconds of CPU work per sample pass')
     p.add_argument('--no-cpu-baseline', action='store_true')
     args = p.parse_args()

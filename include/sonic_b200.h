@@ -22,6 +22,12 @@
  *   sonic_points_run   <- the same for an explicit list of (radius, f, A, Q) points: one
  *                         NeuronalBilayerSonophore.computeEffVars(drive, fs, Qm) call per
  *                         point (nbls.py:153); used by multi-process sharding.
+ *   sonic_lookup_run_multi / sonic_points_run_multi / sonic_plan_create_multi
+ *                      <- the `for name in args['neuron']` loop of scripts/run_lookups.py:193-238 (one
+ *                         computeAStimLookup per neuron): the grids of several neurons go through ONE
+ *                         integrator launch, followed by one averaging launch per neuron.  Trajectories
+ *                         depend on the sonophore constants and |Q| only, so neurons with the same
+ *                         resting charge (same Delta and Lennard-Jones fit, bls.py:49-75) share them.
  *   sonic_plan_*       <- split form of sonic_points_run (upload / launch / fetch) so that a
  *                         caller can keep inputs resident on the device and time the kernels.
  *   sonic_plan_fetch_relcm <- BilayerSonophore.getRelCmCycle (bls.py:806-808) for every point of the
@@ -41,7 +47,7 @@
 extern "C" {
 #endif
 
-#define SONIC_ABI_VERSION 1
+#define SONIC_ABI_VERSION 2
 #define SONIC_ABI_MAX_OVERTONES 4   /* charge overtones per point accepted by the *_ex entry points */
 
 #define SONIC_OK 0
@@ -137,6 +143,27 @@ int sonic_lookup_run(const SonicBlsParams* radii, int na, const double* f, int n
                      int32_t* out_ncycles, uint32_t* out_status, double* out_tpoint,
                      SonicStats* stats);
 
+/* Several neurons in one batch.  radii holds n_neurons blocks of na entries (block k = the
+ * sonophores of neuron_ids[k], which differ in Cm0 and, through the resting charge, in Delta and the
+ * Lennard-Jones fit); neuron k has its own charge vector Qcat[Qoff[k] .. Qoff[k + 1]).
+ *   out_tables : the neurons' blocks one after the other, block k = [1 + nrates_k][na][nf][nA][nQ_k][nfs]
+ *   out_ncycles / out_status / out_tpoint : [sum_k na nf nA nQ_k], same order */
+int sonic_lookup_run_multi(const SonicBlsParams* radii, int na, const double* f, int nf,
+                           const double* A, int nA, const double* Qcat, const int32_t* Qoff,
+                           const double* fs, int nfs, const int32_t* neuron_ids, int n_neurons,
+                           uint32_t device_mask, double* out_tables, int32_t* out_ncycles,
+                           uint32_t* out_status, double* out_tpoint, SonicStats* stats);
+
+/* Explicit point list over several neurons: radius_neuron[na] gives the slot (index into
+ * neuron_ids) each radius entry belongs to, a point's neuron is that of its radius entry.
+ *   out_tables : block k = [1 + nrates_k][n_k][nfs] over the points of neuron slot k in input order;
+ *   per-point outputs [n] in input order. */
+int sonic_points_run_multi(int device, const SonicBlsParams* radii, const int32_t* radius_neuron, int na,
+                           const int32_t* neuron_ids, int n_neurons, int64_t n, const int32_t* ia,
+                           const double* f, const double* A, const double* Q, const double* fs, int nfs,
+                           double* out_tables, int32_t* out_ncycles, uint32_t* out_status,
+                           double* out_tpoint, uint32_t* out_nrhs, SonicStats* stats);
+
 /* Split form: inputs stay resident on the device between launches. */
 typedef struct SonicPlan SonicPlan;
 int sonic_plan_create(int device, const SonicBlsParams* radii, int na, int neuron_id, int64_t n,
@@ -150,6 +177,10 @@ int sonic_plan_create_ex(int device, const SonicBlsParams* radii, int na, int ne
                          const int32_t* ia, const double* f, const double* A, const double* Q,
                          int novertones, const double* overtones, const double* fs, int nfs,
                          SonicPlan** plan);
+int sonic_plan_create_multi(int device, const SonicBlsParams* radii, const int32_t* radius_neuron, int na,
+                            const int32_t* neuron_ids, int n_neurons, int64_t n, const int32_t* ia,
+                            const double* f, const double* A, const double* Q, const double* fs, int nfs,
+                            SonicPlan** plan);
 int sonic_plan_launch(SonicPlan* plan);   /* asynchronous on the plan's stream */
 int sonic_plan_sync(SonicPlan* plan);
 int sonic_plan_fetch(SonicPlan* plan, double* out_tables, int32_t* out_ncycles,
@@ -163,8 +194,9 @@ int sonic_plan_fetch_relcm(SonicPlan* plan, double* out_cm);
 int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
 int sonic_plan_destroy(SonicPlan* plan);
 
-/* Releases the device workspace that one-shot calls keep between invocations (the cycle-profile
- * buffers, up to 8 kB per point): call it when no further lookup will be generated. */
+/* Releases the idle workspaces (one device allocation + one pinned host buffer + stream per plan,
+ * kept per device between calls; up to 8 kB of device memory per point): call it when no further
+ * lookup will be generated. */
 int sonic_trim(void);
 
 /* Sustained FP64 FMA throughput of the device (TFLOP/s), measured with a register-resident

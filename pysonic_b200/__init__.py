@@ -12,7 +12,7 @@ from .bls import BilayerSonophore  # noqa: F401
 from .nbls import NeuronalBilayerSonophore  # noqa: F401
 from .batches import Batch  # noqa: F401
 from .lookups import Lookup  # noqa: F401
-from .run_lookups import computeAStimLookup  # noqa: F401
+from .run_lookups import computeAStimLookup, computeAStimLookups  # noqa: F401
 from .run_cm_lookups import computeCmLookup  # noqa: F401
 
 __version__ = '0.1.0'

@@ -59,6 +59,12 @@ EXPORTS = {
                                     C.c_int, C.POINTER(C.c_void_p)]),
     'sonic_plan_create_ex': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int64, _ip, _dp, _dp, _dp, C.c_int, _dp,
                                        _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    'sonic_plan_create_multi': (C.c_int, [C.c_int, _bp, _ip, C.c_int, _ip, C.c_int, C.c_int64, _ip, _dp, _dp, _dp,
+                                          _dp, C.c_int, C.POINTER(C.c_void_p)]),
+    'sonic_points_run_multi': (C.c_int, [C.c_int, _bp, _ip, C.c_int, _ip, C.c_int, C.c_int64, _ip, _dp, _dp, _dp,
+                                         _dp, C.c_int, _dp, _ip, _up, _dp, _up, _sp]),
+    'sonic_lookup_run_multi': (C.c_int, [_bp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, _ip, _dp, C.c_int, _ip,
+                                         C.c_int, C.c_uint32, _dp, _ip, _up, _dp, _sp]),
     'sonic_plan_set_stream': (C.c_int, [C.c_void_p, C.c_void_p]),
     'sonic_plan_launch': (C.c_int, [C.c_void_p]),
     'sonic_plan_sync': (C.c_int, [C.c_void_p]),
@@ -275,3 +281,38 @@ def lookup_run(bls_params, neuron_id, nrates, f, A, Q, fs, device_mask=1):
                                neuron_id, device_mask, _d(out), ncyc.ctypes.data_as(_ip),
                                status.ctypes.data_as(_up), _d(tpoint), C.byref(st)))
     return out, ncyc, status, tpoint, st.asdict()
+
+
+def lookup_run_multi(bls_params_per_neuron, neuron_ids, nrates, f, A, Qs, fs, device_mask=1):
+    ''' Grids of several neurons in one batch (sonic_lookup_run_multi).
+        :param bls_params_per_neuron: one list of `na` sonophore dicts per neuron
+        :param Qs: one charge vector per neuron
+        :return: list of (tables[1+nrates_k, na, nf, nA, nQ_k, nfs], ncycles, status, tpoint) per neuron, stats '''
+    lib = load()
+    f, A, fs = as_f64(f), as_f64(A), as_f64(fs)
+    Qs = [as_f64(q) for q in Qs]
+    nn = len(neuron_ids)
+    na = len(bls_params_per_neuron[0])
+    assert all(len(b) == na for b in bls_params_per_neuron) and len(Qs) == nn and len(nrates) == nn
+    arr = bls_array([p for b in bls_params_per_neuron for p in b])
+    Qcat = np.concatenate(Qs)
+    Qoff = np.concatenate([[0], np.cumsum([q.size for q in Qs])]).astype(np.int32)
+    ids = np.ascontiguousarray(neuron_ids, dtype=np.int32)
+    dims = [(na, f.size, A.size, q.size) for q in Qs]
+    npts = [int(np.prod(d)) for d in dims]
+    out = np.empty(sum((1 + nr) * n * fs.size for nr, n in zip(nrates, npts)))
+    ncyc = np.empty(sum(npts), dtype=np.int32)
+    status = np.empty(sum(npts), dtype=np.uint32)
+    tpoint = np.empty(sum(npts))
+    st = SonicStats()
+    check(lib.sonic_lookup_run_multi(arr, na, _d(f), f.size, _d(A), A.size, _d(Qcat), Qoff.ctypes.data_as(_ip),
+                                     _d(fs), fs.size, ids.ctypes.data_as(_ip), nn, device_mask, _d(out),
+                                     ncyc.ctypes.data_as(_ip), status.ctypes.data_as(_up), _d(tpoint), C.byref(st)))
+    res, o, q = [], 0, 0
+    for nr, n, d in zip(nrates, npts, dims):
+        m = (1 + nr) * n * fs.size
+        res.append((out[o:o + m].reshape((1 + nr,) + d + (fs.size,)), ncyc[q:q + n].reshape(d),
+                    status[q:q + n].reshape(d), tpoint[q:q + n].reshape(d)))
+        o += m
+        q += n
+    return res, st.asdict()

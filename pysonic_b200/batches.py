@@ -88,6 +88,9 @@ class Batch:
                       (0 if q[3] is None else len(q[3])) == nov0 for q in items)
         if not uniform:
             return [nbls.computeEffVars(q[0], q[1], q[2], q[3]) for q in items]
+        from .nbls import check_drive_phase
+        for q in items:
+            check_drive_phase(q[0])
         f = np.array([q[0].f for q in items])
         A = np.array([q[0].A for q in items])
         Q = np.array([float(q[2]) for q in items])

@@ -10,6 +10,7 @@ import numpy as np
 
 from . import _lib
 from .bls import BilayerSonophore
+from .constants import CHARGE_RANGE, NPC_DENSE
 from .drives import AcousticDrive
 from .neurons import PointNeuron, getPointNeuron
 
@@ -30,6 +31,37 @@ def as_point_neuron(pneuron):
     raise ValueError(f'{pneuron} is not a valid PointNeuron instance')
 
 
+def check_drive_phase(drive):
+    ''' The kernels integrate the reference's default drive phase (phi = pi, drives.py:200): any other
+        phase is refused instead of being silently replaced. '''
+    phi = getattr(drive, 'phi', np.pi)
+    if phi != np.pi:
+        raise ValueError(f'unsupported acoustic drive phase {phi} rad (the lookup path uses phi = pi)')
+
+
+def check_charges(Q, overtones=None):
+    ''' Imposed charges (and the extrema of Fourier-series charge cycles) must lie in the physiological
+        range, with the reference's message (bls.py:674-677 `checkInputs`). '''
+    Qmin, Qmax = CHARGE_RANGE
+    Q = np.atleast_1d(np.asarray(Q, dtype=float))
+    lo, hi = Q, Q
+    if overtones is not None:
+        ov = np.asarray(overtones, dtype=float).reshape(Q.size, -1, 2)
+        swing = 2 * np.abs(ov[:, :, 0]).sum(axis=1)
+        suspect = np.nonzero((Q - swing < Qmin) | (Q + swing > Qmax))[0]
+        lo, hi = Q.copy(), Q.copy()
+        j = np.arange(NPC_DENSE)
+        for i in suspect:      # exact extrema of the sampled cycle, only where the bound is exceeded
+            k = np.arange(1, ov.shape[1] + 1)[:, None]
+            cyc = Q[i] + 2 * (ov[i, :, 0:1] * np.cos(2 * np.pi * j * k / NPC_DENSE + ov[i, :, 1:2])).sum(axis=0)
+            lo[i], hi[i] = cyc.min(), cyc.max()
+    bad = np.nonzero((lo < Qmin) | (hi > Qmax))[0]
+    if bad.size:
+        q = Q[bad[0]]
+        raise ValueError(
+            f'Invalid applied charge: {q * 1e5} nC/cm2 (must be within [{Qmin * 1e5}, {Qmax * 1e5}] interval')
+
+
 class NeuronalBilayerSonophore(BilayerSonophore):
 
     def __init__(self, a, pneuron, embedding_depth=0.0):
@@ -39,12 +71,14 @@ class NeuronalBilayerSonophore(BilayerSonophore):
     def __repr__(self):
         return f'{self.__class__.__name__}({self.a * 1e9:.1f} nm, {self.pneuron})'
 
-    def effvars_batch(self, f, A, Q, fs, device=0, overtones=None):
+    def effvars_batch(self, f, A, Q, fs, device=0, overtones=None, check_charge=True):
         ''' Effective variables for arrays of points (same radius).
             :param overtones: None, or charge overtones [n, novertones, 2] (amplitude C/m2, phase rad)
             :return: (tables[1+2*novertones+nrates, n, nfs], ncycles, status, tpoint, nrhs, stats) '''
         f, A, Q = np.broadcast_arrays(np.asarray(f, float), np.asarray(A, float), np.asarray(Q, float))
         fs = np.atleast_1d(np.asarray(fs, float))
+        if check_charge:
+            check_charges(Q.ravel(), overtones)
         ia = np.zeros(f.size, dtype=np.int32)
         return _lib.points_run(device, [self.abi_params()], self.pneuron.neuron_id,
                                len(self.pneuron.rates), ia, f.ravel(), A.ravel(), Q.ravel(), fs,
@@ -74,6 +108,7 @@ class NeuronalBilayerSonophore(BilayerSonophore):
             ov = np.asarray(Qm_overtones, dtype=float).reshape(1, -1, 2)
         if not isinstance(drive, AcousticDrive) and not (hasattr(drive, 'f') and hasattr(drive, 'A')):
             raise TypeError('Invalid "drive" parameter (must be an "AcousticDrive" object)')
+        check_drive_phase(drive)
         t0 = time.perf_counter()
         fs = np.atleast_1d(np.asarray(fs, dtype=float))
         out, ncyc, status, _, _, _ = self.effvars_batch(drive.f, drive.A, float(Qm0), fs, overtones=ov)

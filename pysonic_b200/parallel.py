@@ -24,23 +24,81 @@ def _cost_table():
     return _COST
 
 
+def _bracket(lx, nodes):
+    ''' Bracketing node indices and weight of log-values `lx` on the ascending log-axis `nodes`
+        (clamped outside). '''
+    i1 = np.clip(np.searchsorted(nodes, lx, side='right'), 1, nodes.size - 1) if nodes.size > 1 else np.zeros(lx.shape, int)
+    i0 = np.maximum(i1 - 1, 0)
+    span = np.where(i1 > i0, nodes[i1] - nodes[i0], 1.0)
+    w = np.clip((lx - nodes[i0]) / span, 0.0, 1.0)
+    return i0, i1, w
+
+
 def predicted_log_cost(a, f, A, Q=None):
-    ''' Same ordering heuristic as the native work queue (sonic_b200.cu: predict_log_cost):
-        nearest node of the measured cost table (tools/make_cost_table.py).  Without charges the
-        envelope over all charges is returned. '''
+    ''' Same ordering heuristic as the native work queue (sonic_b200.cu: predict_log_cost): the
+        measured cost table (tools/make_cost_table.py), interpolated linearly in log(radius) and
+        log(frequency) between its nodes.  Without charges the envelope over all charges is returned. '''
     la, lf, Ae, Qe, tab = _cost_table()
     a, f, A = np.broadcast_arrays(np.asarray(a, float), np.asarray(f, float), np.asarray(A, float))
-    i = np.argmin(np.abs(np.log(a)[..., None] - la), axis=-1)
-    j = np.argmin(np.abs(np.log(f)[..., None] - lf), axis=-1)
+    i0, i1, wi = _bracket(np.log(a), la)
+    j0, j1, wj = _bracket(np.log(f), lf)
     k = np.clip(np.digitize(A, Ae) - 1, 0, tab.shape[2] - 1)
     if Q is None:
-        return tab.max(axis=3)[i, j, k]
-    l = np.clip(np.digitize(np.abs(np.asarray(Q, float)) + 1e-14, Qe) - 1, 0, tab.shape[3] - 1)
-    return tab[i, j, k, l]
+        t = tab.max(axis=3)
+        at = lambda i, j: t[i, j, k]                        # noqa: E731
+    else:
+        l = np.clip(np.digitize(np.abs(np.asarray(Q, float)) + 1e-14, Qe) - 1, 0, tab.shape[3] - 1)
+        at = lambda i, j: tab[i, j, k, l]                   # noqa: E731
+    c0 = at(i0, j0) + wj * (at(i0, j1) - at(i0, j0))
+    c1 = at(i1, j0) + wj * (at(i1, j1) - at(i1, j0))
+    return c0 + wi * (c1 - c0)
+
+
+_OWN_GROUP = False
+
+
+def env_world():
+    ''' (rank, world_size, local_rank) announced by the launcher (torchrun) in the environment. '''
+    return (int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)),
+            int(os.environ.get('LOCAL_RANK', 0)))
+
+
+def init_from_env():
+    ''' Under `torchrun` (RANK / WORLD_SIZE / LOCAL_RANK in the environment): bind this process to
+        its GPU and join the process group (NCCL when a device is present, gloo otherwise), unless the
+        caller has already done so.  Returns (rank, world_size, local_rank).  Outside torchrun: no-op. '''
+    global _OWN_GROUP
+    rank, world, local_rank = env_world()
+    if world <= 1:
+        return 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if cuda:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        else:
+            dist.init_process_group('gloo')
+        _OWN_GROUP = True
+    return rank, world, local_rank
+
+
+def finalize():
+    ''' Leave the process group if `init_from_env` created it. '''
+    global _OWN_GROUP
+    if _OWN_GROUP:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+        _OWN_GROUP = False
 
 
 def dist_info():
-    ''' (rank, world_size, local_rank) of the current process; (0, 1, 0) outside torchrun. '''
+    ''' (rank, world_size, local_rank) of the current process; (0, 1, 0) outside a process group. '''
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -50,10 +108,35 @@ def dist_info():
     return 0, 1, 0
 
 
-def shard_indices(cost, rank, world_size):
-    ''' Indices of the points owned by `rank`: cost-sorted (descending), dealt round-robin. '''
-    order = np.argsort(-np.asarray(cost), kind='stable')
-    return order[rank::world_size]
+def trajectory_groups(ia, f, A, Q):
+    ''' Group id of every point: points that differ by the sign of the charge only share one
+        trajectory (the mechanics see Q^2, bls.py:482-491) and must stay on the same device so that
+        the engine integrates it once.  |Q| is rounded to 36 significant bits exactly as
+        sonic_plan_create_ex does. '''
+    q = np.abs(np.ascontiguousarray(Q, dtype=np.float64))
+    qb = (q.view(np.uint64) + np.uint64(0x8000)) & ~np.uint64(0xFFFF)
+    key = np.stack([np.asarray(ia).astype(np.uint64), np.ascontiguousarray(f, dtype=np.float64).view(np.uint64),
+                    np.ascontiguousarray(A, dtype=np.float64).view(np.uint64), qb], axis=1)
+    _, inv = np.unique(key, axis=0, return_inverse=True)
+    return inv.ravel()
+
+
+def shard_indices(cost, rank, world_size, groups=None):
+    ''' Indices of the points owned by `rank`: cost-sorted (descending), dealt round-robin.  With
+        `groups` (one id per point, equal cost inside a group) whole groups are dealt, so that the
+        +Q / -Q points of a trajectory land on the same rank. '''
+    cost = np.asarray(cost)
+    if groups is None:
+        order = np.argsort(-cost, kind='stable')
+        return order[rank::world_size]
+    groups = np.asarray(groups)
+    first = np.full(groups.max() + 1, -1, dtype=np.int64)
+    first[groups[::-1]] = np.arange(groups.size)[::-1]          # first point of every group
+    gorder = np.argsort(-cost[first], kind='stable')            # groups, most expensive first
+    owner = np.empty(gorder.size, dtype=np.int64)
+    owner[gorder] = np.arange(gorder.size) % world_size
+    idx = np.nonzero(owner[groups] == rank)[0]
+    return idx[np.argsort(-cost[idx], kind='stable')]
 
 
 def gather_slabs(n, idx, arrays, rank, world_size):
@@ -68,7 +151,8 @@ def gather_slabs(n, idx, arrays, rank, world_size):
     import torch
     import torch.distributed as dist
     backend = dist.get_backend()
-    dev = torch.device('cuda', torch.cuda.current_device()) if backend == 'nccl' else torch.device('cpu')
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))) if backend == 'nccl' \
+        else torch.device('cpu')
     # sizes differ by at most one between ranks: pad to the max
     m = int(len(idx))
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world_size)]
@@ -98,7 +182,7 @@ def gather_slabs(n, idx, arrays, rank, world_size):
     return out
 
 
-def run_sharded(compute, n, cost, rank=None, world_size=None):
+def run_sharded(compute, n, cost, rank=None, world_size=None, groups=None):
     ''' Run `compute(idx) -> list of (array, point_axis)` on this rank's shard and gather.
 
         `compute` receives the global indices of the points this rank owns and returns its
@@ -106,7 +190,7 @@ def run_sharded(compute, n, cost, rank=None, world_size=None):
     r, w, _ = dist_info()
     rank = r if rank is None else rank
     world_size = w if world_size is None else world_size
-    idx = shard_indices(cost, rank, world_size)
+    idx = shard_indices(cost, rank, world_size, groups)
     outs = compute(idx)
     if world_size == 1:
         full = []

@@ -83,7 +83,7 @@ def run_point(args):
 
 
 def pmap(jobs, nproc=None):
-    nproc = nproc or mp.cpu_count()
+    nproc = nproc or int(os.environ.get('GOLDEN_NPROC', 0)) or mp.cpu_count()
     with mp.get_context('fork').Pool(nproc) as pool:
         return pool.map(run_point, jobs, chunksize=1)
 
@@ -251,6 +251,34 @@ def gen_c2sub(amp_scale=1.0, tag=''):
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
 
 
+def gen_c2big(amp_scale=1.0, tag=''):
+    ''' Dense subsample of the RS 4-D default grid: every radius, frequency and amplitude (the
+        16 nm / 20 kHz heavy rows included), every 16th charge -> 3 x 7 x 51 x 10 = 10 710 points. '''
+    _grid_to_npz(f'c2_RS_big{tag}.npz', 'RS', [16e-9, 32e-9, 64e-9],
+                 [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], c2_amps(), default_charges('RS')[::16], [1.0],
+                 amp_scale)
+
+
+def gen_neurons_big(amp_scale=1.0, tag=''):
+    ''' >= 1000-point grids for each neuron of BASELINE configs 3-5 (32 nm). '''
+    Aall = c2_amps()
+    for name in ['FHnode', 'SWnode', 'MRGnode', 'SUseg']:
+        Q = default_charges(name)
+        Q = Q[::max(1, Q.size // 12)][:13]
+        _grid_to_npz(f'c4_{name}_big{tag}.npz', name, [32e-9], [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6],
+                     Aall[[0, 8, 16, 22, 28, 32, 36, 40, 43, 46, 48, 50]], Q, [1.0], amp_scale)
+    for name in ['RE', 'TC']:
+        pn = getPointNeuron(name)
+        Qmin, Qmax = pn.Qbounds
+        Q = np.arange(Qmin, Qmax + 5e-6, 5e-6)
+        A = np.logspace(np.log10(50), np.log10(600), 26) * 1e3
+        _grid_to_npz(f'c5_{name}_big{tag}.npz', name, [32e-9], [20e3, 500e3, 4e6],
+                     A[::2], Q[::max(1, Q.size // 26)][:27], [1.0], amp_scale)
+    Q = default_charges('STN')
+    _grid_to_npz(f'c3_STN_big{tag}.npz', 'STN', [32e-9], [500e3], Aall[::2],
+                 Q[::4], np.arange(1, 101)[::11] * 1e-2, amp_scale)
+
+
 def gen_cortical(amp_scale=1.0, tag=''):
     ''' Small grids for the other cortical neurons that share the RS kinetics family (FS, LTS, IB):
         two radii, three frequencies, five amplitudes, six charges. '''
@@ -328,8 +356,12 @@ if __name__ == '__main__':
                                               (1.0 - 8.881784197001252e-16, '_ulp_dn2'))],
             'cortical': lambda: (gen_cortical(), gen_cortical(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                  gen_cortical(1.0 - 4.440892098500626e-16, '_ulp_dn')), 'overtones': gen_overtones, 'noise': gen_noise,
+            'c2big': lambda: (gen_c2big(), gen_c2big(1.0 + 4.440892098500626e-16, '_ulp_up'),
+                              gen_c2big(1.0 - 4.440892098500626e-16, '_ulp_dn')),
+            'neurons_big': lambda: (gen_neurons_big(), gen_neurons_big(1.0 + 4.440892098500626e-16, '_ulp_up'),
+                                    gen_neurons_big(1.0 - 4.440892098500626e-16, '_ulp_dn')),
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4')):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4', 'c2big', 'neurons_big')):
             fn()

@@ -40,7 +40,7 @@ def test_neuron_registry(build):
     from pysonic_b200 import _lib
     from pysonic_b200.neurons import NEURON_ORDER, spec_rate_names
     lib = _lib.load()
-    assert lib.sonic_version() == 1
+    assert lib.sonic_version() == 2
     assert lib.sonic_neuron_count() == len(NEURON_ORDER)
     for i, name in enumerate(NEURON_ORDER):
         assert lib.sonic_neuron_id(name.encode()) == i

@@ -235,6 +235,82 @@ def test_c2_against_subsample_goldens(c2_full):
         assert np.mean(err > RTOL) < 0.05
 
 
+def _need(fname):
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    for t in ('.npz', '_ulp_up.npz', '_ulp_dn.npz'):
+        if not os.path.isfile(os.path.join(here, fname.replace('.npz', t))):
+            pytest.skip(f'fixture {fname.replace(".npz", t)} not generated yet (tests/golden/make_goldens.py)')
+
+
+def _variants(fname):
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    return [load_grid(fname.replace('.npz', t)) for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz')
+            if os.path.isfile(os.path.join(here, fname.replace('.npz', t)))]
+
+
+def test_c2_full_against_dense_goldens(c2_full):
+    ''' The full RS 4-D table at the nodes of the dense reference fixture: every radius, frequency
+        and amplitude (the 16 nm / 20 kHz heavy rows included) x every 16th charge = 10 710 points. '''
+    w, lkp, info = c2_full
+    _need('c2_RS_big.npz')
+    g = load_grid('c2_RS_big.npz')
+    v = _variants('c2_RS_big.npz')
+    keys = [str(k) for k in g['keys']]
+    iQ = [int(np.argmin(np.abs(w['Q'] - x))) for x in g['Q']]
+    assert np.array_equal(w['A'], g['A']) and np.array_equal(w['Q'][iQ], g['Q']) and np.array_equal(w['f'], g['f'])
+    sub = {k: lkp[k][:, :, :, iQ] for k in keys}
+    nc = info['ncycles'][:, :, :, iQ]
+    assert_grid_parity(sub, nc, g, v[0], v[1], keys, 'C2 full @ dense fixture nodes', more=v[2:])
+
+
+@pytest.mark.parametrize('fname', ['c3_STN_big.npz', 'c4_FHnode_big.npz', 'c4_SWnode_big.npz',
+                                   'c4_MRGnode_big.npz', 'c4_SUseg_big.npz', 'c5_RE_big.npz', 'c5_TC_big.npz'])
+def test_other_neuron_dense_grids(gpu, fname):
+    ''' >= 1000-point reference fixtures for every neuron of BASELINE configs 3-5. '''
+    _need(fname)
+    g = load_grid(fname)
+    v = _variants(fname)
+    keys = [str(k) for k in g['keys']]
+    lkp, info = _lookup(g)
+    assert_grid_parity(lkp.tables, info['ncycles'], g, v[0], v[1], keys, fname, more=v[2:])
+
+
+def test_sharded_halves_are_bit_identical(gpu, c2_full):
+    ''' The multi-GPU partition on one device: the RS 4-D table computed as the two world_size = 2
+        shards of `parallel.shard_indices` (what each rank integrates under torchrun), scattered as
+        `run_sharded` does, equals the unsharded table bit for bit. '''
+    ps = _ps()
+    from pysonic_b200.parallel import predicted_log_cost, shard_indices, trajectory_groups
+    w, lkp, info = c2_full
+    pn = ps.getPointNeuron('RS')
+    ia, f, A, Q = np.meshgrid(np.arange(w['a'].size), w['f'], w['A'], w['Q'], indexing='ij')
+    ia, f, A, Q = [x.ravel() for x in (ia, f, A, Q)]
+    cost = predicted_log_cost(w['a'][ia], f, A, Q)
+    groups = trajectory_groups(ia, f, A, Q)
+    bls = [ps.NeuronalBilayerSonophore(float(a), pn).abi_params() for a in w['a']]
+    nvar = 1 + len(pn.rates)
+    full = np.zeros((nvar, ia.size, 1))
+    ncyc = np.zeros(ia.size, np.int32)
+    seen = np.zeros(ia.size, int)
+    nrhs = 0
+    for rank in range(2):
+        idx = shard_indices(cost, rank, 2, groups)
+        # both signs of a charge travel together: no trajectory group is split between the ranks
+        assert not np.isin(groups[idx], groups[np.setdiff1d(np.arange(ia.size), idx)]).any()
+        out, nc, st, tp, nr, stats = gpu.points_run(0, bls, pn.neuron_id, len(pn.rates), ia[idx].astype(np.int32),
+                                                    f[idx], A[idx], Q[idx], w['fs'])
+        full[:, idx] = out
+        ncyc[idx] = nc
+        seen[idx] += 1
+        nrhs += stats['n_rhs']
+    assert np.all(seen == 1)
+    for v, k in enumerate(['V'] + pn.rates):
+        np.testing.assert_array_equal(full[v].reshape(lkp[k].shape), lkp[k])
+    np.testing.assert_array_equal(ncyc.reshape(info['ncycles'].shape), info['ncycles'])
+    # trajectories are not split between the shards: same integrator work as the unsharded run
+    assert nrhs == info['stats']['n_rhs']
+
+
 def test_results_do_not_depend_on_batching(gpu, c2_full):
     ''' A point gives bit-identical results alone, in a permuted explicit list, and in the grid:
         lanes are independent and the work-queue order cannot leak into the numbers. '''
@@ -297,11 +373,13 @@ def test_edge_cases(gpu):
     assert lkp['V'].shape == (1, 2, 2, 2, 1)
     np.testing.assert_array_equal(lkp.refs['f'], [500e3, 2e6])
     # a charge with no quasi-static equilibrium is reported, not silently integrated
-    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, 10.0, 1.0)
+    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, 10.0, 1.0, check_charge=False)
+    with pytest.raises(ValueError, match='Invalid applied charge'):
+        nbls.effvars_batch(500e3, 1e5, 10.0, 1.0)           # bls.py:674-677
     assert (status[0] & 16) and ncyc[0] == 0 and np.isnan(out).all()
     # an absurd charge that the integrator cannot follow is flagged (step failure / excess work),
     # its outputs are NaN, and the other points of the batch are unaffected
-    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, np.array([1.0, -71.9e-5]), 1.0)
+    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, np.array([1.0, -71.9e-5]), 1.0, check_charge=False)
     assert (status[0] & (4 | 8 | 16)) and np.isnan(out[:, 0]).all()
     assert status[1] == 0 and out[0, 1, 0] == pytest.approx(-136.78744984747215, rel=RTOL)
     # empty list and bad arguments are errors of the C ABI, not crashes
@@ -542,3 +620,37 @@ def test_robustness_outside_the_baseline_grids(gpu):
         assert np.isfinite(out[:, ok]).all()
         assert np.isnan(out[:, ~ok]).all()
         assert np.all((ncyc[ok] >= 2) & (ncyc[ok] <= 11))
+
+
+def test_multi_neuron_batch_is_bit_identical(gpu):
+    ''' computeAStimLookups: the grids of several neurons through one integrator launch (the neuron loop
+        of scripts/run_lookups.py:193-238) give the single-neuron tables bit for bit; FS and IB have
+        the same resting charge, hence the same sonophore constants, and share every trajectory. '''
+    ps = _ps()
+    names = ['RS', 'FS', 'LTS', 'IB']
+    pns = [ps.getPointNeuron(n) for n in names]
+    a, f = np.array([16e-9, 32e-9]), np.array([100e3, 500e3, 2e6])
+    A = np.array([0., 2e3, 5e4, 3e5])
+    fs = np.array([1.0])
+    Qs = [np.arange(pn.Qbounds[0], pn.Qbounds[1] + 1e-5, 1e-5)[::9] for pn in pns]
+    lkps, info = ps.computeAStimLookups(pns, a, f, A, fs, Qs, return_info=True, loglevel=10)
+    n_rhs_single = 0
+    for pn, Q, lkp, inf in zip(pns, Qs, lkps, info['neurons']):
+        one, i1 = ps.computeAStimLookup(pn, a, f, A, fs, Q, return_info=True, loglevel=10)
+        assert list(lkp.tables.keys()) == list(one.tables.keys())
+        assert list(lkp.refs.keys()) == list(one.refs.keys())
+        for k in ['V'] + pn.rates:
+            np.testing.assert_array_equal(lkp[k], one[k], err_msg=f'{pn.name} {k}')
+        np.testing.assert_array_equal(inf['ncycles'], i1['ncycles'])
+        np.testing.assert_array_equal(inf['status'], i1['status'])
+        n_rhs_single += i1['stats']['n_rhs']
+    # FS and IB: one set of trajectories for both
+    assert info['stats']['n_rhs'] < n_rhs_single
+    assert info['stats']['n_points'] == sum(a.size * f.size * A.size * Q.size for Q in Qs)
+    # coverage sweep in a multi-neuron batch
+    fs2 = np.array([0.25, 0.5, 1.0])
+    lk2 = ps.computeAStimLookups(pns[:2], a[:1], f[1:2], A, fs2, [Q[::3] for Q in Qs[:2]], loglevel=10)
+    for pn, Q, lkp in zip(pns[:2], Qs[:2], lk2):
+        one = ps.computeAStimLookup(pn, a[:1], f[1:2], A, fs2, Q[::3], loglevel=10)
+        for k in ['V'] + pn.rates:
+            np.testing.assert_array_equal(lkp[k], one[k])

@@ -178,3 +178,90 @@ def test_cm_lookup_validation_and_names():
         ps.computeCmLookup(bls, np.array([-1.]), np.array([0., 1e5]))
     with pytest.raises(ValueError):
         ps.computeCmLookup(bls, np.array([5e5]), np.array([-1.]))
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: grid-shaping rules of the overtone lookup, input validation, trajectory-aware sharding
+# ---------------------------------------------------------------------------------------------
+def _lookup_refs_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lookup_refs.json')) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize('case', ['overtones1_default', 'overtones1_test', 'overtones2_small', 'plain_test', 'fs_span'])
+def test_refs_match_reference_front_end(case):
+    ''' Keys, order, sizes and values of `refs` against the reference's computeAStimLookup
+        (scripts/run_lookups.py:48-128; fixture made by tests/golden/make_lookup_refs.py). '''
+    from pysonic_b200.run_lookups import build_refs, overtone_refs
+    c = _lookup_refs_golden()[case]
+    a = c['args']
+    refs = build_refs(np.array(a['a']), np.array(a['f']), np.array(a['A']), np.array(a['fs']), np.array(a['Q']),
+                      novertones=a['novertones'], test=a['test'])
+    if a['novertones']:
+        refs = overtone_refs(refs, a['novertones'], a['test'])
+    assert list(refs.keys()) == list(c['refs'].keys())
+    for k, v in c['refs'].items():
+        np.testing.assert_array_equal(refs[k], np.array(v), err_msg=k)
+    assert [x.size for x in refs.values()] == c['shape']
+
+
+def test_overtone_lookup_refuses_several_radii():
+    from pysonic_b200.run_lookups import build_refs
+    msg = _lookup_refs_golden()['overtones_multi_a_error']
+    A = np.array([0., 1e4])
+    with pytest.raises(AssertionError) as e:
+        build_refs(np.array([16e-9, 32e-9]), np.array([500e3]), A, np.array([1.0]), np.array([0.]), novertones=1)
+    assert str(e.value) == msg
+    with pytest.raises(AssertionError):
+        build_refs(np.array([32e-9]), np.array([500e3, 1e6]), A, np.array([1.0]), np.array([0.]), novertones=1)
+    with pytest.raises(AssertionError):
+        build_refs(np.array([32e-9]), np.array([500e3]), A, np.array([0.5, 1.0]), np.array([0.]), novertones=1)
+
+
+def test_charge_range_and_phase_checks():
+    ''' bls.py:674-677: charges (and the extrema of Fourier-series charge cycles) outside
+        CHARGE_RANGE raise ValueError; a non-default drive phase is refused, not ignored. '''
+    from pysonic_b200.nbls import check_charges, check_drive_phase
+    check_charges(np.array([-300e-5, 0., 150e-5]))
+    with pytest.raises(ValueError, match='Invalid applied charge'):
+        check_charges(np.array([0., -301e-5]))
+    with pytest.raises(ValueError, match='Invalid applied charge'):
+        check_charges(151e-5)
+    # cycle Q0 + 2 A cos(.): -107 - 2 x 100 nC/cm2 leaves the range, -107 - 2 x 50 does not
+    check_charges(np.array([-107e-5]), np.array([[[50e-5, 0.]]]))
+    with pytest.raises(ValueError, match='Invalid applied charge'):
+        check_charges(np.array([-107e-5]), np.array([[[100e-5, 0.]]]))
+    check_drive_phase(ps.AcousticDrive(500e3, 1e5))
+    with pytest.raises(ValueError, match='phase'):
+        check_drive_phase(ps.AcousticDrive(500e3, 1e5, phi=0.5))
+    nbls = ps.NeuronalBilayerSonophore(32e-9, ps.getPointNeuron('RS'))
+    with pytest.raises(ValueError, match='phase'):
+        nbls.computeEffVars(ps.AcousticDrive(500e3, 1e5, phi=0.), 1.0, -71.9e-5)
+
+
+def test_sharding_keeps_both_signs_of_a_charge_together():
+    from pysonic_b200.parallel import trajectory_groups
+    a = np.array([16e-9, 32e-9, 64e-9])
+    Qv = np.arange(-107e-5, 50e-5 + 1e-5, 1e-5)
+    ia, f, A, Q = np.meshgrid(np.arange(3), [2e4, 5e5, 4e6], [0., 1e4, 3e5], Qv, indexing='ij')
+    ia, f, A, Q = [x.ravel() for x in (ia, f, A, Q)]
+    groups = trajectory_groups(ia, f, A, Q)
+    # 158 charges of np.arange: 50 of them have a mirror image -> 108 trajectories per (a, f, A)
+    assert groups.max() + 1 == 27 * 108
+    cost = predicted_log_cost(a[ia], f, A, Q)
+    for world in (2, 3, 8):
+        owner = np.full(ia.size, -1)
+        for r in range(world):
+            idx = shard_indices(cost, r, world, groups)
+            assert np.all(owner[idx] == -1)
+            owner[idx] = r
+            assert np.all(np.diff(cost[idx]) <= 0)           # most expensive first
+        assert np.all(owner >= 0)
+        for g in range(groups.max() + 1):
+            assert np.unique(owner[groups == g]).size == 1
+        # balanced: the predicted work of the ranks differs by a few percent at most
+        work = np.array([np.exp(cost[owner == r]).sum() for r in range(world)])
+        assert work.max() / work.min() < 1.1
+    # without groups: plain cost-sorted round-robin
+    np.testing.assert_array_equal(shard_indices(cost, 1, 2), np.argsort(-cost, kind='stable')[1::2])

@@ -96,3 +96,49 @@ def test_single_process_path():
     ref = _fake_compute(a, f, A, Q, fs)
     np.testing.assert_array_equal(out, ref[0])
     np.testing.assert_array_equal(ncyc, ref[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# the command line under a launcher (torchrun sets RANK / WORLD_SIZE / LOCAL_RANK): main() joins the
+# process group itself, every rank integrates its shard, rank 0 alone writes the pickle
+# ---------------------------------------------------------------------------------------------
+def _fake_points_run(device, bls, neuron_id, nrates, ia, f, A, Q, fs, overtones=None):
+    n = f.size
+    base = np.sin(f * 1e-6) + np.log1p(A) + Q * 1e3 + np.array([b['a'] for b in bls])[ia] * 1e9
+    out = np.stack([np.outer(base * (v + 1), fs) for v in range(1 + nrates)])
+    ncyc = (3 + (A == 0) * 8).astype(np.int32)
+    status = (A == 0).astype(np.uint32)
+    return out, ncyc, status, base * 1e-3, np.full(n, 7 + device, np.uint32), {'n_points': n}
+
+
+def _main_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from pysonic_b200 import _lib, run_lookups
+    _lib.points_run = _fake_points_run            # no GPU here: stand-in for the native call
+    run_lookups.main(['-n', 'RS', '-a', '16', '32', '-f', '500', '2000', '-A', '0', '50', '300',
+                      '-Q', '-50', '0', '50', '--mpi', '-o', outdir, '-y'])
+    assert not dist.is_initialized()              # main() leaves the group it created
+
+
+def test_cli_under_launcher_shards_and_writes_once(tmp_path):
+    sys.path.insert(0, ROOT)
+    world = 2
+    mp.spawn(_main_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ['RS_lookups_fs1.00.pkl'], files
+    import pickle
+    with open(tmp_path / 'RS_lookups_fs1.00.pkl', 'rb') as fh:
+        d = pickle.load(fh)
+    assert list(d['refs']) == ['a', 'f', 'A', 'Q', 'fs']
+    a, f, A, Q = d['refs']['a'], d['refs']['f'], d['refs']['A'], d['refs']['Q']
+    ia, fi, Ai, Qi = [x.ravel() for x in np.meshgrid(np.arange(a.size), f, A, Q, indexing='ij')]
+    import pysonic_b200 as ps
+    pn = ps.getPointNeuron('RS')
+    bls = [{'a': x} for x in a]
+    ref = _fake_points_run(0, bls, 0, len(pn.rates), ia, fi, Ai, Qi, d['refs']['fs'])
+    assert list(d['tables']) == ['V'] + pn.rates + ['tcomp']
+    for v, k in enumerate(['V'] + pn.rates):
+        np.testing.assert_array_equal(d['tables'][k], ref[0][v].reshape(2, 2, 3, 3, 1))
+    np.testing.assert_array_equal(d['tables']['tcomp'][..., 0], ref[3].reshape(2, 2, 3, 3))
