@@ -32,6 +32,8 @@
  *                         caller can keep inputs resident on the device and time the kernels.
  *   sonic_plan_fetch_relcm <- BilayerSonophore.getRelCmCycle (bls.py:806-808) for every point of the
  *                         plan: what scripts/run_Cm_lookups.py:19-64 tabulates.
+ *   sonic_pmavg        <- BilayerSonophore.PMavg / v_PMavg (bls.py:390-408): the quadrature behind the
+ *                         Lennard-Jones fit of computePMparams (bls.py:410-470), batched over Z.
  *   sonic_mean_rates   <- PointNeuron.getEffRates(Vm) (pneuron.py:268-271).
  *   sonic_eval_rates   <- the neuron's alphax/betax/xinf/taux methods evaluated elementwise
  *                         (PySONIC/neurons/*.py), for testing the generated device functions.
@@ -193,6 +195,13 @@ int sonic_plan_fetch_zprofiles(SonicPlan* plan, double* out_z);
 int sonic_plan_fetch_relcm(SonicPlan* plan, double* out_cm);
 int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
 int sonic_plan_destroy(SonicPlan* plan);
+
+/* Average intermolecular pressure PMavg(Z) (Pa) of a sonophore of radius a and gap Delta for n
+ * deflections Z (m): BilayerSonophore.v_PMavg (bls.py:390-408).  The caller supplies a Gauss-Legendre
+ * rule on [-1, 1] (nodes, weights, nnode <= 64) and an even panel count; out_err (optional) receives
+ * the difference with the same rule on npanel / 2 panels. */
+int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, const double* nodes,
+                const double* weights, int nnode, int npanel, double* out_pm, double* out_err);
 
 /* Releases the idle workspaces (one device allocation + one pinned host buffer + stream per plan,
  * kept per device between calls; up to 8 kB of device memory per point): call it when no further

@@ -9,6 +9,79 @@ import numpy as np
 
 from .constants import Rg
 
+LJFIT_PM_MAX = 1e8        # Pm at the lower deflection bound of the LJ fit (Pa)      constants.py:21
+PNET_EQ_MAX = 1e-1        # residual pressure allowed at the equilibrium gap (Pa)     constants.py:22
+PMAVG_STD_ERR_MAX = 5e3   # standard error allowed for the LJ fit (Pa)                constants.py:23
+
+_computed = {}            # (radius key, charge key) -> [Delta, x0, C, nrep, nattr] computed in this process
+
+
+def LennardJones(x, beta, alpha, C, m, n):
+    ''' Lennard-Jones function of a symmetric deflection x (bls.py:29-41). '''
+    u = alpha / (2 * x + beta)
+    return C * (np.power(u, m) - np.power(u, n))
+
+
+def brentq(f, a, b, xtol=2e-12, rtol=8.881784197001252e-16, maxiter=100):
+    ''' Root of f on a sign-changing bracket [a, b]: the classic bracketing combination of inverse
+        quadratic interpolation, secant and bisection steps (Brent), with the stopping rule
+        |half bracket| < (xtol + rtol |x|) / 2 that the reference relies on through
+        scipy.optimize.brentq (bls.py:423,504,573). '''
+    xpre, xcur = float(a), float(b)
+    fpre, fcur = f(xpre), f(xcur)
+    if fpre * fcur > 0:
+        raise ValueError('f(a) and f(b) must have different signs')
+    if fpre == 0:
+        return xpre
+    if fcur == 0:
+        return xcur
+    xblk = fblk = spre = scur = 0.0
+    for _ in range(maxiter):
+        if fpre != 0 and fcur != 0 and (np.sign(fpre) != np.sign(fcur)):
+            xblk, fblk = xpre, fpre
+            spre = scur = xcur - xpre
+        if abs(fblk) < abs(fcur):
+            xpre, xcur, xblk = xcur, xblk, xcur
+            fpre, fcur, fblk = fcur, fblk, fcur
+        delta = (xtol + rtol * abs(xcur)) / 2
+        sbis = (xblk - xcur) / 2
+        if fcur == 0 or abs(sbis) < delta:
+            return xcur
+        if abs(spre) > delta and abs(fcur) < abs(fpre):
+            if xpre == xblk:
+                stry = -fcur * (xcur - xpre) / (fcur - fpre)
+            else:
+                dpre = (fpre - fcur) / (xpre - xcur)
+                dblk = (fblk - fcur) / (xblk - xcur)
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre))
+            if 2 * abs(stry) < min(abs(spre), 3 * abs(sbis) - delta):
+                spre, scur = scur, stry
+            else:
+                spre = scur = sbis
+        else:
+            spre = scur = sbis
+        xpre, fpre = xcur, fcur
+        xcur += scur if abs(scur) > delta else (delta if sbis > 0 else -delta)
+        fcur = f(xcur)
+    raise RuntimeError('root finder failed to converge')
+
+
+def lj_least_squares(Z, P, Delta, pguess):
+    ''' Nonlinear least-squares fit of the Lennard-Jones function to P(Z) from the reference's initial
+        guess.  The reference calls scipy.optimize.curve_fit (bls.py:438-441), i.e. MINPACK's
+        Levenberg-Marquardt `lmdif` with a forward-difference Jacobian and ftol = xtol = 1.49e-8; the
+        parameters sit in a flat valley of the cost for small radii, so where that algorithm stops is
+        part of the result: the same MINPACK routine is called here (through scipy.optimize.leastsq,
+        with curve_fit's settings) on the GPU-computed pressures.  A 4-parameter host-side solve. '''
+    from scipy.optimize import leastsq       # third-party MINPACK binding, as in the reference
+    Z = np.asarray(Z, dtype=float)
+    P = np.asarray(P, dtype=float)
+    popt, ier = leastsq(lambda p: LennardJones(Z, Delta, *p) - P, pguess, maxfev=100000)
+    if ier not in (1, 2, 3, 4):
+        raise RuntimeError('Optimal parameters not found')
+    return popt
+
+
 _TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'bls_params.json')
 _rows = None
 
@@ -44,19 +117,101 @@ class BilayerSonophore:
         self.V0 = np.pi * self.Delta * self.a**2
         self.ng0 = self.P0 * self.V0 / (Rg * self.T)
 
+    # biomechanical constants of the intermolecular pressure (bls.py:89-97,108-109)
+    delta0 = 2.0e-9      # thickness of the leaflet (m)
+    Delta_ = 1.4e-9      # gap between the leaflets of a non-charged membrane at equilibrium (m)
+    pDelta = 1.0e5       # attraction / repulsion pressure coefficient (Pa)
+    m = 5.0              # exponent of the repulsion term
+    n = 3.3              # exponent of the attraction term
+    epsilon0 = 8.854e-12
+    epsilonR = 1.0
+
     def computePMparams(self):
-        ''' Equilibrium gap and Lennard-Jones fit of the intermolecular pressure, read from the
-            table of precomputed values (same keys as bls.py:49-75). '''
+        ''' Equilibrium gap and Lennard-Jones fit of the average intermolecular pressure
+            (bls.py:457-470).  Like the reference (its `@lookup` cache, bls.py:44-76) the values are read
+            from a table of precomputed results when the (radius, resting charge) pair is known --
+            `data/bls_params.json` holds the reference's own cache -- and computed otherwise:
+            `findDeltaEq` then `LJfitPMavg`, with the quadratures on the GPU. '''
         akey = f'{self.a * 1e9:.1f}'
         Qkey = f'{self.Qm0 * 1e5:.2f}'
-        try:
-            Delta, x0, C, nrep, nattr = _table()[(akey, Qkey)]
-        except KeyError:
-            raise ValueError(
-                f'no precomputed intermolecular-pressure fit for a = {akey} nm, '
-                f'Qm0 = {Qkey} nC/cm2 (available in {_TABLE})')
+        row = _table().get((akey, Qkey)) or _computed.get((akey, Qkey))
+        if row is None:
+            if self.Qm0 == 0.0:
+                self.Delta = self.Delta_
+            else:
+                self.Delta, Pnet_eq = self.findDeltaEq(self.Qm0)
+                assert Pnet_eq < PNET_EQ_MAX, 'High Pnet at Z = 0 with ∆ = %.2f nm' % (self.Delta * 1e9)
+            self.LJ_approx, std_err, _ = self.LJfitPMavg()
+            assert std_err < PMAVG_STD_ERR_MAX, 'High error in PmAvg nonlinear fit: std_err =  %.2f Pa' % std_err
+            _computed[(akey, Qkey)] = [self.Delta] + [self.LJ_approx[k] for k in ('x0', 'C', 'nrep', 'nattr')]
+            return
+        Delta, x0, C, nrep, nattr = row
         self.Delta = Delta
         self.LJ_approx = {'x0': x0, 'C': C, 'nrep': nrep, 'nattr': nattr}
+
+    def curvrad(self, Z):
+        ''' Leaflet curvature radius, signed (bls.py:286-296). '''
+        return np.inf if Z == 0.0 else (self.a**2 + Z**2) / (2 * Z)
+
+    def surface(self, Z):
+        ''' Surface area of the stretched leaflet (bls.py:302-309). '''
+        return np.pi * (self.a**2 + Z**2)
+
+    def Pelec(self, Z, Qm):
+        ''' Electrical pressure term (bls.py:482-491). '''
+        relS = self.S0 / self.surface(Z)
+        return -relS * Qm**2 / (2 * self.epsilon0 * self.epsilonR)
+
+    def findDeltaEq(self, Qm):
+        ''' Gap that cancels the intermolecular + electrical pressure at Z = 0 for a given charge
+            density, and the residual pressure there (bls.py:493-506; same bracket and tolerance). '''
+        def dualPressure(Delta):
+            x = self.Delta_ / Delta
+            return self.pDelta * (x**self.m - x**self.n) + self.Pelec(0.0, Qm)
+        Delta_eq = brentq(dualPressure, 0.1 * self.Delta_, 2.0 * self.Delta_, xtol=1e-16)
+        return Delta_eq, dualPressure(Delta_eq)
+
+    def v_PMavg(self, Z, device=0):
+        ''' Average intermolecular pressure across the leaflet (Pa) for an array of deflections
+            (bls.py:390-408): batched quadrature on the GPU, accuracy checked against a coarser rule. '''
+        from . import _lib
+        pm, err = _lib.pmavg(self.a, self.Delta, Z, device=device, with_error=True)
+        bad = err > 1e-9 * np.maximum(np.abs(pm), 1.0)
+        if bad.any():           # refine where the two rules disagree
+            pm2, err2 = _lib.pmavg(self.a, self.Delta, np.asarray(Z)[bad], device=device, nnode=32, npanel=256,
+                                   with_error=True)
+            if (err2 > 1e-8 * np.maximum(np.abs(pm2), 1.0)).any():
+                raise ArithmeticError('intermolecular pressure quadrature did not converge')
+            pm[bad] = pm2
+        return pm
+
+    def PMavg(self, Z, R=None, S=None):
+        ''' Average intermolecular pressure (Pa) at one deflection; R and S are accepted for
+            signature compatibility with bls.py:390 (they are functions of Z). '''
+        return float(self.v_PMavg(np.array([Z]))[0])
+
+    def LJfitPMavg(self, pmavg=None):
+        ''' Lennard-Jones parameters approximating the average intermolecular pressure between the
+            deflection where it reaches LJFIT_PM_MAX and twice the radius (bls.py:410-455).
+
+            :param pmavg: optional replacement for `v_PMavg` (testing)
+            :return: (LJ parameters, standard error and max error of the fit in Pa) '''
+        pmavg = pmavg or self.v_PMavg
+        # lower bound of the deflection range: where Pm = Pmmax
+        Zlb = brentq(lambda Z: float(pmavg(np.array([Z]))[0]) - LJFIT_PM_MAX, self.Zmin, 0.0, xtol=1e-16)
+        Z = np.arange(Zlb, 2 * self.a, 1e-11)
+        Pm = np.asarray(pmavg(Z), dtype=float)
+        pguess = (self.delta0, 0.1 * self.pDelta, self.m, self.n)
+        popt = lj_least_squares(Z, Pm, self.Delta, pguess)
+        res = Pm - LennardJones(Z, self.Delta, *popt)
+        std_err = float(np.sqrt(np.sum(res**2) / res.size))
+        LJ_approx = dict(zip(('x0', 'C', 'nrep', 'nattr'), map(float, popt)))
+        return LJ_approx, std_err, float(np.max(np.abs(res)))
+
+    def PMavgpred(self, Z):
+        ''' Fitted average intermolecular pressure (bls.py:472-480). '''
+        return LennardJones(Z, self.Delta, self.LJ_approx['x0'], self.LJ_approx['C'],
+                            self.LJ_approx['nrep'], self.LJ_approx['nattr'])
 
     @property
     def Zmin(self):

@@ -457,7 +457,7 @@ def test_plan_relaunch_is_deterministic(gpu):
     st = plan.stats()
     plan.destroy()
     assert z.shape == (n, 1000) and np.isfinite(z).all()
-    assert st['n_points'] == n and st['n_launches'] == 6 and st['ms_integrate'] > 0
+    assert st['n_points'] == n and st['n_launches'] == 8 and st['ms_integrate'] > 0   # z0, integrator, averaging, counters
     # V recomputed on the host from the device profiles equals the device average
     b = so.get_bls('RS', 32e-9)
     for i in (0, 17, 63):
@@ -654,3 +654,65 @@ def test_multi_neuron_batch_is_bit_identical(gpu):
         one = ps.computeAStimLookup(pn, a[:1], f[1:2], A, fs2, Q[::3], loglevel=10)
         for k in ['V'] + pn.rates:
             np.testing.assert_array_equal(lkp[k], one[k])
+
+
+# ---------------------------------------------------------------------------------------------
+# intermolecular-pressure parameters for radii outside the parameter table
+# ---------------------------------------------------------------------------------------------
+def _ljfit_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ljfit.json')) as fh:
+        return json.load(fh)
+
+
+def test_pmavg_quadrature_matches_reference(gpu):
+    ''' sonic_pmavg (GPU Gauss-Legendre quadrature) against BilayerSonophore.PMavg (scipy quad,
+        bls.py:390-404) from large negative deflections to twice the radius. '''
+    recs = _ljfit_golden()['pmavg']
+    by = {}
+    for r in recs:
+        by.setdefault((r['a'], r['Delta']), []).append(r)
+    assert len(by) >= 7
+    for (a, Delta), rows in by.items():
+        Z = np.array([r['Z'] for r in rows])
+        ref = np.array([r['PMavg'] for r in rows])
+        pm, err = gpu.pmavg(a, Delta, Z, with_error=True)
+        assert np.all(np.abs(pm - ref) <= 1e-9 * np.abs(ref) + 1e-6), (a, np.max(np.abs(pm / ref - 1)))
+        assert np.all(err <= 1e-9 * np.abs(pm) + 1e-6)
+
+
+def test_computePMparams_for_radii_outside_the_table(gpu):
+    ''' findDeltaEq + LJfitPMavg (bls.py:410-506) for (radius, resting charge) pairs absent from the
+        reference's cache: the gap is bit-identical, the Lennard-Jones parameters agree to 1e-6 or
+        to the reference's own reproducibility where that is worse (the parameters sit in a flat
+        valley of the cost for small radii; `self_noise` = the reference re-run with its quadrature
+        values perturbed by 1e-13), and the fitted pressure curves coincide far below the fit error. '''
+    ps = _ps()
+    from pysonic_b200.bls import BilayerSonophore, LennardJones, _table
+    strict = 0
+    for rec in _ljfit_golden()['fits']:
+        assert (f"{rec['a'] * 1e9:.1f}", f"{rec['Qm0'] * 1e5:.2f}") not in _table()
+        b = BilayerSonophore(rec['a'], 1e-2, rec['Qm0'])
+        assert b.Delta == rec['Delta']
+        tol = max(1e-6, 5 * rec['self_noise'])
+        for k in ('x0', 'C', 'nrep', 'nattr'):
+            assert abs(b.LJ_approx[k] - rec[k]) <= tol * abs(rec[k]), (rec['a'], rec['Qm0'], k, b.LJ_approx[k], rec[k])
+        strict += tol <= 3e-6
+        Z = np.linspace(-0.3 * b.Delta, 2 * rec['a'], 2000)
+        mine = b.PMavgpred(Z)
+        ref = LennardJones(Z, rec['Delta'], rec['x0'], rec['C'], rec['nrep'], rec['nattr'])
+        assert np.max(np.abs(mine - ref)) <= 1e-6 * np.max(np.abs(ref)) + 1e-3
+    assert strict >= 5
+    # a table row recomputed from scratch (the reference authors' own cached result)
+    row = _table()[('32.0', '-71.90')]
+    b = BilayerSonophore.__new__(BilayerSonophore)
+    b.a, b.Qm0, b.S0 = 32e-9, -71.9e-5, np.pi * 32e-9**2
+    b.Delta, _ = b.findDeltaEq(b.Qm0)
+    assert b.Delta == pytest.approx(row[0], rel=1e-12)
+    LJ, std_err, _ = b.LJfitPMavg()
+    for k, v in zip(('x0', 'C', 'nrep', 'nattr'), row[1:]):
+        assert LJ[k] == pytest.approx(v, rel=2e-5), k
+    # and the lookup path runs on such a sonophore
+    nbls = ps.NeuronalBilayerSonophore(50e-9, ps.getPointNeuron('RE'))
+    ev, _ = nbls.computeEffVars(ps.AcousticDrive(700e3, 80e3), 1.0, -89.5e-5)
+    assert np.isfinite(ev[0]['V']) and ev[0]['V'] < 0

@@ -43,8 +43,12 @@ def test_rates_golden_neurons_all_declared(rates_golden):
 def test_unknown_neuron_and_radius():
     with pytest.raises(ValueError):
         ps.getPointNeuron('XYZ')
-    with pytest.raises(ValueError, match='no precomputed'):
-        ps.NeuronalBilayerSonophore(33.3e-9, ps.getPointNeuron('RS'))
+    # a radius absent from the parameter table is computed (findDeltaEq + LJfitPMavg with the
+    # quadratures on the GPU): without a device that fails loudly, there is no CPU path
+    from pysonic_b200 import _lib
+    if _lib.device_count() == 0:
+        with pytest.raises(_lib.SonicError, match='no CUDA device'):
+            ps.NeuronalBilayerSonophore(33.3e-9, ps.getPointNeuron('RS'))
     with pytest.raises(ValueError):
         ps.BilayerSonophore(-1e-9, 1e-2, -7e-4)
 
@@ -265,3 +269,63 @@ def test_sharding_keeps_both_signs_of_a_charge_together():
         assert work.max() / work.min() < 1.1
     # without groups: plain cost-sorted round-robin
     np.testing.assert_array_equal(shard_indices(cost, 1, 2), np.argsort(-cost, kind='stable')[1::2])
+
+
+# ---------------------------------------------------------------------------------------------
+# intermolecular-pressure parameters: host logic of findDeltaEq / LJfitPMavg
+# ---------------------------------------------------------------------------------------------
+def _ljfit_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ljfit.json')) as fh:
+        return json.load(fh)
+
+
+def test_brentq_matches_scipy():
+    from scipy.optimize import brentq as sbrentq
+    from pysonic_b200.bls import brentq
+    for f, a, b in [(lambda x: x**3 - 2 * x - 5, 2., 3.), (lambda x: np.cos(x) - x, 0., 1.),
+                    (lambda x: np.exp(-x) - 1e-3, 0., 20.), (lambda x: (x - 1e-9) * 1e9, -1e-8, 1e-8)]:
+        assert brentq(f, a, b, xtol=1e-16) == sbrentq(f, a, b, xtol=1e-16)
+    with pytest.raises(ValueError):
+        brentq(lambda x: x * x + 1, -1., 1.)
+
+
+def test_equilibrium_gap_is_bit_identical():
+    ''' findDeltaEq (bls.py:493-506) for charges absent from the parameter table. '''
+    from pysonic_b200.bls import BilayerSonophore
+    for rec in _ljfit_golden()['fits']:
+        if rec['Qm0'] == 0.0:
+            continue
+        b = BilayerSonophore.__new__(BilayerSonophore)
+        b.a, b.Qm0, b.S0 = rec['a'], rec['Qm0'], np.pi * rec['a']**2
+        D, P = b.findDeltaEq(rec['Qm0'])
+        assert D == rec['Delta_eq'] and P == rec['Pnet_eq']
+
+
+def test_lj_fit_host_logic_with_cpu_quadrature():
+    ''' LJfitPMavg with the quadrature replaced by scipy.integrate.quad (the GPU quadrature is tested
+        with -m gpu): bracket search, deflection grid and fit reproduce the reference parameters to
+        the reference's own reproducibility. '''
+    from scipy import integrate
+    from pysonic_b200.bls import BilayerSonophore
+
+    def make_pmavg(b):
+        def one(Z):
+            R, S = b.curvrad(Z), b.surface(Z)
+
+            def g(r):
+                z = 0.0 if Z == 0 else np.sign(Z) * (np.sqrt(R**2 - r**2) - abs(R) + abs(Z))
+                rel = (2 * z + b.Delta) / b.Delta_
+                return 2 * np.pi * r * b.pDelta * ((1 / rel)**b.m - (1 / rel)**b.n)
+            return integrate.quad(g, 0, b.a)[0] / S
+        return lambda Z: np.array([one(z) for z in np.atleast_1d(Z)])
+
+    for rec in _ljfit_golden()['fits'][:1] + _ljfit_golden()['fits'][5:]:
+        b = BilayerSonophore.__new__(BilayerSonophore)
+        b.a, b.Qm0, b.S0 = rec['a'], rec['Qm0'], np.pi * rec['a']**2
+        b.Delta = rec['Delta']
+        LJ, std_err, max_err = b.LJfitPMavg(pmavg=make_pmavg(b))
+        tol = max(1e-6, 5 * rec['self_noise'])
+        for k in ('x0', 'C', 'nrep', 'nattr'):
+            assert abs(LJ[k] - rec[k]) <= tol * abs(rec[k]), (rec['a'], k, LJ[k], rec[k])
+        assert std_err < 5e3
