@@ -197,11 +197,10 @@ int sonic_plan_stats(SonicPlan* plan, SonicStats* stats);
 int sonic_plan_destroy(SonicPlan* plan);
 
 /* Average intermolecular pressure PMavg(Z) (Pa) of a sonophore of radius a and gap Delta for n
- * deflections Z (m): BilayerSonophore.v_PMavg (bls.py:390-408).  The caller supplies a Gauss-Legendre
- * rule on [-1, 1] (nodes, weights, nnode <= 64) and an even panel count; out_err (optional) receives
- * the difference with the same rule on npanel / 2 panels. */
-int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, const double* nodes,
-                const double* weights, int nnode, int npanel, double* out_pm, double* out_err);
+ * deflections Z (m): BilayerSonophore.v_PMavg (bls.py:390-408), i.e. scipy.integrate.quad (QUADPACK
+ * QAGS, epsabs = epsrel = 1.49e-8, 50 sub-intervals at most) of the leaflet force 2 pi r PMlocal(r) over
+ * [0, a], divided by the stretched surface.  out_last (optional): sub-intervals used per deflection. */
+int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, double* out_pm, int32_t* out_last);
 
 /* Releases the idle workspaces (one device allocation + one pinned host buffer + stream per plan,
  * kept per device between calls; up to 8 kB of device memory per point): call it when no further

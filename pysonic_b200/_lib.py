@@ -73,7 +73,7 @@ EXPORTS = {
     'sonic_plan_fetch_relcm': (C.c_int, [C.c_void_p, _dp]),
     'sonic_plan_stats': (C.c_int, [C.c_void_p, _sp]),
     'sonic_plan_destroy': (C.c_int, [C.c_void_p]),
-    'sonic_pmavg': (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int64, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _dp]),
+    'sonic_pmavg': (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int64, _dp, _dp, _ip]),
     'sonic_trim': (C.c_int, []),
     'sonic_fp64_peak': (C.c_int, [C.c_int, _dp]),
 }
@@ -319,18 +319,12 @@ def lookup_run_multi(bls_params_per_neuron, neuron_ids, nrates, f, A, Qs, fs, de
     return res, st.asdict()
 
 
-_GL = {}
-
-
-def pmavg(a, Delta, Z, device=0, nnode=16, npanel=32, with_error=False):
-    ''' Average intermolecular pressure (Pa) at deflections Z (sonic_pmavg: composite Gauss-Legendre
-        quadrature on the GPU, one warp per deflection). '''
+def pmavg(a, Delta, Z, device=0, with_last=False):
+    ''' Average intermolecular pressure (Pa) at deflections Z (sonic_pmavg: one QAGS run per deflection
+        on the GPU, the sequence of rules scipy.integrate.quad applies in the reference). '''
     lib = load()
-    if nnode not in _GL:
-        _GL[nnode] = tuple(as_f64(v) for v in np.polynomial.legendre.leggauss(nnode))
-    x, w = _GL[nnode]
     Z = as_f64(np.atleast_1d(Z)).ravel()
     out = np.empty(Z.size)
-    err = np.empty(Z.size)
-    check(lib.sonic_pmavg(device, float(a), float(Delta), Z.size, _d(Z), _d(x), _d(w), nnode, npanel, _d(out), _d(err)))
-    return (out, err) if with_error else out
+    last = np.empty(Z.size, dtype=np.int32)
+    check(lib.sonic_pmavg(device, float(a), float(Delta), Z.size, _d(Z), _d(out), last.ctypes.data_as(_ip)))
+    return (out, last) if with_last else out

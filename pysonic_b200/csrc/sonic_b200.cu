@@ -49,6 +49,7 @@
 #include "generated/cost_table.h"
 #include "generated/neuron_rates.cuh"
 #include "sonic_core.h"
+#include "sonic_quad.h"
 
 // ---------------------------------------------------------------------------------------
 // error handling
@@ -432,50 +433,15 @@ __global__ void __launch_bounds__(256) sonic_relcm_kernel(const double* __restri
     }
 }
 
-// Average intermolecular pressure over the leaflet (bls.py:373-404): PMavg(Z) = (1 / S) int_0^a 2 pi r
-// PMlocal(r, Z, R) dr with PMlocal = pDelta ((Delta* / gap)^m - (Delta* / gap)^n), gap = 2 z(r) + Delta and
-// z(r) the local deflection of the spherical cap (bls.py:359-371).  The reference integrates with QUADPACK
-// (scipy.integrate.quad); here one warp per deflection value evaluates a composite Gauss-Legendre rule
-// (`npanel` panels x `nnode` nodes, nodes and weights supplied by the caller) and, for the error
-// estimate, the same rule on half as many panels.
-__global__ void __launch_bounds__(128) sonic_pmavg_kernel(double a, double Delta, long long n, const double* __restrict__ Z,
-                                                          const double* __restrict__ xg, const double* __restrict__ wg,
-                                                          int nnode, int npanel, double* __restrict__ out,
-                                                          double* __restrict__ err) {
-    const double pDelta = 1.0e5, Delta_ = 1.4e-9, m_att = 3.3;      // bls.py:92-97 (m = 5 is expanded below)
-    const int lane = threadIdx.x & 31;
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long i = w; i < n; i += nw) {
-        const double z0 = Z[i];
-        const double R = z0 == 0.0 ? INFINITY : (a * a + z0 * z0) / (2.0 * z0);      // bls.py:286-296
-        const double S = SONIC_PI * (a * a + z0 * z0);                                // bls.py:302-309
-        const double sg = z0 > 0.0 ? 1.0 : -1.0;
-        double acc[2] = {0.0, 0.0};
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            const int np = pass == 0 ? npanel : npanel / 2;
-            const double hw = 0.5 * a / np;                       // panel half width
-            double sum = 0.0;
-            for (int k = lane; k < np * nnode; k += 32) {
-                const int pnl = k / nnode, j = k - pnl * nnode;
-                const double r = (2 * pnl + 1) * hw + hw * xg[j];
-                double zl = 0.0;
-                if (z0 != 0.0) zl = sg * (sqrt(R * R - r * r) - fabs(R) + fabs(z0));
-                const double u = 1.0 / ((2.0 * zl + Delta) / Delta_);
-                const double u2 = u * u;
-                const double pm = pDelta * (u2 * u2 * u - pow(u, m_att));
-                sum += wg[j] * (2.0 * SONIC_PI * r * pm);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            acc[pass] = sum * hw;
-        }
-        if (lane == 0) {
-            out[i] = acc[0] / S;
-            if (err) err[i] = fabs(acc[0] - acc[1]) / S;
-        }
-    }
+// Average intermolecular pressure PMavg(Z) (bls.py:390-408), one thread per deflection value: each runs the
+// QAGS sequence of scipy.integrate.quad on the leaflet force integrand (sonic_quad.h).
+__global__ void __launch_bounds__(64) sonic_pmavg_kernel(double a, double Delta, long long n, const double* __restrict__ Z,
+                                                         double* __restrict__ out, int* __restrict__ last) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = 0;
+    out[i] = sonic_pmavg_point(a, Delta, Z[i], &l);
+    if (last) last[i] = l;
 }
 
 // FP64 FMA peak: 8 independent register chains per thread.
@@ -1635,32 +1601,23 @@ int sonic_lookup_run_multi(const SonicBlsParams* radii, int na, const double* f,
                          out_ncycles, out_status, out_tpoint, stats);
 }
 
-int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, const double* nodes,
-                const double* weights, int nnode, int npanel, double* out_pm, double* out_err) {
+int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, double* out_pm, int32_t* out_last) {
     int rc = check_device(device);
     if (rc) return rc;
-    if (!(a > 0.) || !(Delta > 0.) || n <= 0 || !Z || !nodes || !weights || nnode < 2 || nnode > 64 || npanel < 2 ||
-        (npanel & 1) || !out_pm)
-        return set_err(SONIC_E_ARG, "invalid argument (a, Delta > 0; n > 0; 2 <= nnode <= 64; npanel even)");
+    if (!(a > 0.) || !(Delta > 0.) || n <= 0 || !Z || !out_pm)
+        return set_err(SONIC_E_ARG, "invalid argument (a, Delta > 0; n > 0; Z and out_pm required)");
     CUDA_TRY(cudaSetDevice(device));
-    double *d_Z = nullptr, *d_x = nullptr, *d_w = nullptr, *d_out = nullptr;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_Z), (3 * (size_t)n + 2 * (size_t)nnode) * sizeof(double));
+    double* d_Z = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_Z), (size_t)n * (2 * sizeof(double) + sizeof(int)));
+    double* d_out = d_Z + n;
+    int* d_last = reinterpret_cast<int*>(d_out + n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_Z, Z, n * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        d_out = d_Z + n;
-        d_x = d_out + 2 * n;
-        d_w = d_x + nnode;
-        e = cudaMemcpy(d_Z, Z, n * sizeof(double), cudaMemcpyHostToDevice);
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(d_x, nodes, nnode * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_w, weights, nnode * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        long long blocks = (n * 32 + 127) / 128;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        sonic_pmavg_kernel<<<(int)blocks, 128>>>(a, Delta, n, d_Z, d_x, d_w, nnode, npanel, d_out, d_out + n);
+        sonic_pmavg_kernel<<<(unsigned)((n + 63) / 64), 64>>>(a, Delta, n, d_Z, d_out, d_last);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(out_pm, d_out, n * sizeof(double), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && out_err) e = cudaMemcpy(out_err, d_out + n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_last) e = cudaMemcpy(out_last, d_last, n * sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(d_Z);
     if (e != cudaSuccess) return set_err(SONIC_E_CUDA, "intermolecular pressure quadrature failed: %s", cudaGetErrorString(e));
     return SONIC_OK;

@@ -8,6 +8,7 @@
 
 #define SONIC_TRACE 1
 #include "../../pysonic_b200/csrc/sonic_core.h"
+#include "../../pysonic_b200/csrc/sonic_quad.h"
 
 static SonicTables g_tab;
 static int g_tab_ready = 0;
@@ -131,6 +132,33 @@ double hostsim_z0(const double* bls, double f, double A, double Q) {
     double z0 = 0.;
     sonic_z0(p, f, &z0);
     return z0;
+}
+
+// average intermolecular pressure with the QAGS restatement (sonic_quad.h), and the bare quadrature of
+// a few test integrands (kind 0: sqrt(x), 1: log(x + 1e-9), 2: 1 / sqrt(|x - 0.3| + 1e-6), 3: exp(-50 (x - 0.7)^2),
+// 4: sin(30 x) / (x + 0.01), 5: |x - 0.5|^0.3) for comparison with scipy.integrate.quad
+void hostsim_pmavg(double a, double Delta, long n, const double* Z, double* out, int* last) {
+    for (long i = 0; i < n; i++) out[i] = sonic_pmavg_point(a, Delta, Z[i], last + i);
+}
+
+struct HostsimTestIntegrand {
+    int kind;
+    double operator()(double x) const {
+        switch (kind) {
+            case 0: return sqrt(x);
+            case 1: return log(x + 1e-9);
+            case 2: return 1.0 / sqrt(fabs(x - 0.3) + 1e-6);
+            case 3: return exp(-50.0 * (x - 0.7) * (x - 0.7));
+            case 4: return sin(30.0 * x) / (x + 0.01);
+            default: return pow(fabs(x - 0.5), 0.3);
+        }
+    }
+};
+
+double hostsim_quad(int kind, double a, double b, int* last) {
+    HostsimTestIntegrand f;
+    f.kind = kind;
+    return sonic_qags(f, a, b, last);
 }
 
 long hostsim_tables_size(void) { return (long)(sizeof(SonicTables) / sizeof(double)); }

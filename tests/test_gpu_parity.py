@@ -666,8 +666,10 @@ def _ljfit_golden():
 
 
 def test_pmavg_quadrature_matches_reference(gpu):
-    ''' sonic_pmavg (GPU Gauss-Legendre quadrature) against BilayerSonophore.PMavg (scipy quad,
-        bls.py:390-404) from large negative deflections to twice the radius. '''
+    ''' sonic_pmavg (one QAGS run per deflection on the GPU) against BilayerSonophore.PMavg
+        (scipy.integrate.quad, bls.py:390-404) from large negative deflections to twice the radius:
+        the same sequence of quadrature rules, hence the same (partly unconverged) values up to the
+        rounding of the device's pow. '''
     recs = _ljfit_golden()['pmavg']
     by = {}
     for r in recs:
@@ -676,9 +678,9 @@ def test_pmavg_quadrature_matches_reference(gpu):
     for (a, Delta), rows in by.items():
         Z = np.array([r['Z'] for r in rows])
         ref = np.array([r['PMavg'] for r in rows])
-        pm, err = gpu.pmavg(a, Delta, Z, with_error=True)
-        assert np.all(np.abs(pm - ref) <= 1e-9 * np.abs(ref) + 1e-6), (a, np.max(np.abs(pm / ref - 1)))
-        assert np.all(err <= 1e-9 * np.abs(pm) + 1e-6)
+        pm, last = gpu.pmavg(a, Delta, Z, with_last=True)
+        assert np.all(np.abs(pm - ref) <= 1e-12 * np.abs(ref)), (a, np.max(np.abs(pm / ref - 1)))
+        assert last.min() >= 1 and last.max() <= 50
 
 
 def test_computePMparams_for_radii_outside_the_table(gpu):

@@ -230,3 +230,34 @@ def test_charge_overtones(hostsim):
                     e = max(e, float(rel_err(ev[k], refev[k])))
         bad += (e > RTOL) or (h['ncycles'] != p['ncycles']) or h['status'] != 0
     assert bad <= 2, bad
+
+
+def test_qags_restatement_is_bitwise_scipy_quad(hostsim, points_golden):
+    ''' csrc/sonic_quad.h (QK21 / QAGSE / QELG / QPSRT restated from QUADPACK's published algorithm)
+        against scipy.integrate.quad: identical results and sub-interval counts on integrands that
+        exercise bisection, the extrapolation table and its restarts; then the average intermolecular
+        pressure (bls.py:390-404) against values produced by the reference itself. '''
+    import json
+    import os
+    from scipy import integrate
+    lib = hostsim.lib
+    lib.hostsim_quad.restype = ctypes.c_double
+    cases = [(lambda x: np.sqrt(x), 0., 1.), (lambda x: np.log(x + 1e-9), 0., 1.),
+             (lambda x: 1 / np.sqrt(abs(x - 0.3) + 1e-6), 0., 1.), (lambda x: np.exp(-50 * (x - 0.7) * (x - 0.7)), 0., 1.),
+             (lambda x: np.sin(30 * x) / (x + 0.01), 0., 2.), (lambda x: abs(x - 0.5)**0.3, 0., 1.)]
+    for k, (f, a, b) in enumerate(cases):
+        last = ctypes.c_int()
+        v = lib.hostsim_quad(ctypes.c_int(k), ctypes.c_double(a), ctypes.c_double(b), ctypes.byref(last))
+        q, _, info = integrate.quad(f, a, b, full_output=1)[:3]
+        assert v == q and last.value == info['last'], (k, v, q, last.value, info['last'])
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ljfit.json')) as fh:
+        recs = json.load(fh)['pmavg']
+    dp = ctypes.POINTER(ctypes.c_double)
+    nlast = set()
+    for r in recs:
+        Z, out, last = np.array([r['Z']]), np.zeros(1), np.zeros(1, np.int32)
+        lib.hostsim_pmavg(ctypes.c_double(r['a']), ctypes.c_double(r['Delta']), ctypes.c_long(1), Z.ctypes.data_as(dp),
+                          out.ctypes.data_as(dp), last.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+        assert abs(out[0] - r['PMavg']) <= 4.5e-16 * abs(r['PMavg']), r
+        nlast.add(int(last[0]))
+    assert len(nlast) >= 2          # accepted at the first rule for some deflections, bisected for others
