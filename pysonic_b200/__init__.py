@@ -7,7 +7,7 @@
 
 from .constants import *  # noqa: F401,F403
 from .drives import AcousticDrive  # noqa: F401
-from .neurons import PointNeuron, getPointNeuron  # noqa: F401
+from .neurons import PointNeuron, getDefaultPassiveNeuron, getPointNeuron, passiveNeuron  # noqa: F401
 from .bls import BilayerSonophore  # noqa: F401
 from .nbls import NeuronalBilayerSonophore  # noqa: F401
 from .batches import Batch  # noqa: F401

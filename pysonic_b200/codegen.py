@@ -60,6 +60,7 @@ def gen_neuron(nid, name):
             i += 1
     for k in spec['consts']:
         lines.append(f'        (void){k};')
+    lines.append('        (void)Vm; (void)r;')
     lines += ['    }', '};', '']
     return '\n'.join(lines)
 

@@ -2,7 +2,7 @@
 // Voltage-dependent rate constants (s^-1) of every supported point neuron, as device functions.
 #pragma once
 
-#define SONIC_N_NEURONS 11
+#define SONIC_N_NEURONS 16
 #define SONIC_MAX_RATES 18
 
 // x / (exp(x / y) - 1): naive form of the reference (pneuron.py:351-354), 0/0 at x = 0 kept.
@@ -28,6 +28,7 @@ template <> struct SonicRates<0> {
         r[7] = (1 - inf_p) / tau_p;
         (void)VT;
         (void)TauMax;
+        (void)Vm; (void)r;
     }
 };
 
@@ -49,6 +50,7 @@ template <> struct SonicRates<1> {
         r[7] = (1 - inf_p) / tau_p;
         (void)VT;
         (void)TauMax;
+        (void)Vm; (void)r;
     }
 };
 
@@ -81,6 +83,7 @@ template <> struct SonicRates<2> {
         (void)VT;
         (void)TauMax;
         (void)Vx;
+        (void)Vm; (void)r;
     }
 };
 
@@ -106,6 +109,7 @@ template <> struct SonicRates<3> {
         r[11] = 0.0065 / (exp(-(Vm + 15) / 28) + 1) * 1e3;
         (void)VT;
         (void)TauMax;
+        (void)Vm; (void)r;
     }
 };
 
@@ -129,6 +133,7 @@ template <> struct SonicRates<4> {
         r[8] = inf_u / tau_u;
         r[9] = (1 - inf_u) / tau_u;
         (void)VT;
+        (void)Vm; (void)r;
     }
 };
 
@@ -159,6 +164,7 @@ template <> struct SonicRates<5> {
         r[11] = (1 - inf_o) / tau_o;
         (void)VT;
         (void)Vx;
+        (void)Vm; (void)r;
     }
 };
 
@@ -202,6 +208,7 @@ template <> struct SonicRates<6> {
         const double tau_q = 0.0 + 0.4 / (exp(-(Vm - (-50)) / (-15)) + exp(-(Vm - (-50)) / (16)));
         r[16] = inf_q / tau_q;
         r[17] = (1 - inf_q) / tau_q;
+        (void)Vm; (void)r;
     }
 };
 
@@ -221,6 +228,7 @@ template <> struct SonicRates<7> {
         r[7] = q10 * 0.09 * vtrap(Vm - V0 + 25., 20.) * 1e3;
         (void)q10;
         (void)V0;
+        (void)Vm; (void)r;
     }
 };
 
@@ -234,6 +242,7 @@ template <> struct SonicRates<8> {
         r[1] = am / (exp((Vm + 56.2) / 4.17));
         r[2] = bh / exp((Vm + 74.5) / 5);
         r[3] = bh;
+        (void)Vm; (void)r;
     }
 };
 
@@ -257,6 +266,7 @@ template <> struct SonicRates<9> {
         (void)q10_mp;
         (void)q10_h;
         (void)q10_s;
+        (void)Vm; (void)r;
     }
 };
 
@@ -284,12 +294,94 @@ template <> struct SonicRates<10> {
         (void)q10BG;
         (void)FARADAY;
         (void)RgT;
+        (void)Vm; (void)r;
     }
 };
 
-static const char* const SONIC_NEURON_NAMES[SONIC_N_NEURONS] = {"RS", "FS", "LTS", "IB", "RE", "TC", "STN", "FHnode", "SWnode", "MRGnode", "SUseg"};
-static const int SONIC_NEURON_NRATES[SONIC_N_NEURONS] = {8, 8, 12, 12, 10, 12, 18, 8, 4, 8, 8};
-static const double SONIC_NEURON_CM0[SONIC_N_NEURONS] = {0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.02, 0.025, 0.02, 0.01};
+// ---- HHseg ----
+template <> struct SonicRates<11> {
+    static constexpr int N = 6;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double q10 = 26.1246286895632;
+        r[0] = q10 * 0.1 * vtrap(-(Vm + 40), 10) * 1e3;
+        r[1] = q10 * 4 * exp(-(Vm + 65) / 18) * 1e3;
+        r[2] = q10 * 0.07 * exp(-(Vm + 65) / 20) * 1e3;
+        r[3] = q10 * 1.0 / (exp(-(Vm + 35) / 10) + 1) * 1e3;
+        r[4] = q10 * 0.01 * vtrap(-(Vm + 55), 10) * 1e3;
+        r[5] = q10 * 0.125 * exp(-(Vm + 65) / 80) * 1e3;
+        (void)q10;
+        (void)Vm; (void)r;
+    }
+};
+
+// ---- LeechT ----
+template <> struct SonicRates<12> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double hb = 1 + exp((Vm - (-50.0)) / 9.0);
+        const double inf_m = 1 / (1 + exp((Vm - (-35.0)) / (-5.0)));
+        const double tau_m = 0.1e-3;
+        r[0] = inf_m / tau_m;
+        r[1] = (1 - inf_m) / tau_m;
+        const double inf_h = 1 / (hb * hb);
+        const double tau_h = (14.0e-3 - 0.2e-3) / (1 + exp((Vm - (-36.0)) / 3.5)) + 0.2e-3;
+        r[2] = inf_h / tau_h;
+        r[3] = (1 - inf_h) / tau_h;
+        const double inf_n = 1 / (1 + exp((Vm - (-22.0)) / (-9.0)));
+        const double tau_n = (6.0e-3 - 1.0e-3) / (1 + exp((Vm - (-10.0)) / 10.0)) + 1.0e-3;
+        r[4] = inf_n / tau_n;
+        r[5] = (1 - inf_n) / tau_n;
+        const double inf_s = 1 / (1 + exp((Vm - (-10.0)) / (-2.8)));
+        const double tau_s = 0.6e-3;
+        r[6] = inf_s / tau_s;
+        r[7] = (1 - inf_s) / tau_s;
+        (void)Vm; (void)r;
+    }
+};
+
+// ---- LeechP ----
+template <> struct SonicRates<13> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        r[0] = -0.03 * (Vm + 28) / (exp(-(Vm + 28) / 15) - 1) * 1e3;
+        r[1] = 2.7 * exp(-(Vm + 53) / 18) * 1e3;
+        r[2] = 0.045 * exp(-(Vm + 58) / 18) * 1e3;
+        r[3] = 0.72 / (exp(-(Vm + 23) / 14) + 1) * 1e3;
+        r[4] = -0.024 * (Vm - 17) / (exp(-(Vm - 17) / 8) - 1) * 1e3;
+        r[5] = 0.2 * exp(-(Vm + 48) / 35) * 1e3;
+        r[6] = -1.5 * (Vm - 20) / (exp(-(Vm - 20) / 5) - 1) * 1e3;
+        r[7] = 1.5 * exp(-(Vm + 25) / 10) * 1e3;
+        (void)Vm; (void)r;
+    }
+};
+
+// ---- template ----
+template <> struct SonicRates<14> {
+    static constexpr int N = 6;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        const double VT = -56.2;
+        r[0] = 0.32 * vtrap(13 - (Vm - VT), 4) * 1e3;
+        r[1] = 0.28 * vtrap((Vm - VT) - 40, 5) * 1e3;
+        r[2] = 0.128 * exp(-((Vm - VT) - 17) / 18) * 1e3;
+        r[3] = 4 / (1 + exp(-((Vm - VT) - 40) / 5)) * 1e3;
+        r[4] = 0.032 * vtrap(15 - (Vm - VT), 5) * 1e3;
+        r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
+        (void)VT;
+        (void)Vm; (void)r;
+    }
+};
+
+// ---- pas ----
+template <> struct SonicRates<15> {
+    static constexpr int N = 0;
+    static __device__ __forceinline__ void eval(const double Vm, double* r) {
+        (void)Vm; (void)r;
+    }
+};
+
+static const char* const SONIC_NEURON_NAMES[SONIC_N_NEURONS] = {"RS", "FS", "LTS", "IB", "RE", "TC", "STN", "FHnode", "SWnode", "MRGnode", "SUseg", "HHseg", "LeechT", "LeechP", "template", "pas"};
+static const int SONIC_NEURON_NRATES[SONIC_N_NEURONS] = {8, 8, 12, 12, 10, 12, 18, 8, 4, 8, 8, 6, 8, 8, 6, 0};
+static const double SONIC_NEURON_CM0[SONIC_N_NEURONS] = {0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.02, 0.025, 0.02, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01};
 static const char* const SONIC_NEURON_RATE_NAMES[SONIC_N_NEURONS][SONIC_MAX_RATES] = {
     {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
     {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
@@ -301,6 +393,11 @@ static const char* const SONIC_NEURON_RATE_NAMES[SONIC_N_NEURONS][SONIC_MAX_RATE
     {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphap", "betap", "", "", "", "", "", "", "", "", "", ""},
     {"alpham", "betam", "alphah", "betah", "", "", "", "", "", "", "", "", "", "", "", "", "", ""},
     {"alpham", "betam", "alphah", "betah", "alphap", "betap", "alphas", "betas", "", "", "", "", "", "", "", "", "", ""},
-    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphal", "betal", "", "", "", "", "", "", "", "", "", ""}
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphal", "betal", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "", "", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphas", "betas", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "alphas", "betas", "", "", "", "", "", "", "", "", "", ""},
+    {"alpham", "betam", "alphah", "betah", "alphan", "betan", "", "", "", "", "", "", "", "", "", "", "", ""},
+    {"", "", "", "", "", "", "", "", "", "", "", "", "", "", "", "", "", ""}
 };
-#define SONIC_DISPATCH_NEURON(id, CALL) switch (id) { case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; default: break; }
+#define SONIC_DISPATCH_NEURON(id, CALL) switch (id) { case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break; case 14: CALL(14); break; case 15: CALL(15); break; default: break; }

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(Son
                         const double q = nov ? sonic_charge_sample(q0, nov, ovp, k) : q0;
                         // spatial average of the capacitance, then membrane potential in mV
                         const double vm = q / (x * cm[k] + (1 - x) * b.Cm0) * 1e3;   // nbls.py:148-151,188
-                        double r[NR];
+                        double r[NR > 0 ? NR : 1];
                         SonicRates<NID>::eval(vm, r);
                         acc[0] += vm;
                         // Fourier coefficients of the potential, rfft(Vm)[m] (nbls.py:194-201)
@@ -383,7 +383,7 @@ __global__ void sonic_rates_kernel(const double* __restrict__ vm, long long n, d
     constexpr int NR = SonicRates<NID>::N;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
          k += (long long)gridDim.x * blockDim.x) {
-        double r[NR];
+        double r[NR > 0 ? NR : 1];
         SonicRates<NID>::eval(vm[k], r);
 #pragma unroll
         for (int v = 0; v < NR; v++) out[(long long)v * n + k] = r[v];
@@ -395,12 +395,13 @@ template <int NID>
 __global__ void __launch_bounds__(256) sonic_mean_rates_kernel(const double* __restrict__ vm, long long n,
                                                               double* __restrict__ out) {
     constexpr int NR = SonicRates<NID>::N;
-    __shared__ double part[8][NR];
-    double acc[NR];
+    constexpr int NS = NR > 0 ? NR : 1;
+    __shared__ double part[8][NS];
+    double acc[NS];
 #pragma unroll
     for (int v = 0; v < NR; v++) acc[v] = 0.0;
     for (long long k = threadIdx.x; k < n; k += blockDim.x) {
-        double r[NR];
+        double r[NS];
         SonicRates<NID>::eval(vm[k], r);
 #pragma unroll
         for (int v = 0; v < NR; v++) acc[v] += r[v];
@@ -1174,6 +1175,7 @@ static int rates_common(int device, int id, const double* Vm, int64_t n, double*
     if (!Vm || !out || n <= 0) return set_err(SONIC_E_ARG, "invalid Vm/out/n");
     CUDA_TRY(cudaSetDevice(device));
     const int nr = SONIC_NEURON_NRATES[id];
+    if (nr == 0) return SONIC_OK;          // passive membrane: no rate constant
     double *d_vm = nullptr, *d_out = nullptr;
     const size_t nout = mean ? (size_t)nr : (size_t)nr * n;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_vm), n * sizeof(double));

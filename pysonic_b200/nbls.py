@@ -12,7 +12,7 @@ from . import _lib
 from .bls import BilayerSonophore
 from .constants import CHARGE_RANGE, NPC_DENSE
 from .drives import AcousticDrive
-from .neurons import PointNeuron, getPointNeuron
+from .neurons import PointNeuron, check_foreign_neuron, getPointNeuron
 
 logger = logging.getLogger('pysonic_b200')
 
@@ -27,7 +27,7 @@ def as_point_neuron(pneuron):
     if isinstance(pneuron, str):
         return getPointNeuron(pneuron)
     if hasattr(pneuron, 'name'):
-        return getPointNeuron(pneuron.name)
+        return check_foreign_neuron(pneuron, getPointNeuron(pneuron.name))
     raise ValueError(f'{pneuron} is not a valid PointNeuron instance')
 
 
@@ -122,7 +122,7 @@ class NeuronalBilayerSonophore(BilayerSonophore):
         ''' nbls.py:224-241 '''
         if all(x is None for x in [a, f, A, fs]):
             fs = 1.
-        fname = f'{self.pneuron.name}_lookups'
+        fname = f"{getattr(self.pneuron, 'lookup_name', self.pneuron.name)}_lookups"
         if a is not None:
             fname += f'_{a * 1e9:.0f}nm'
         if f is not None:

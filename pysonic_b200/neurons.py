@@ -18,6 +18,8 @@
     SURVEY.md Appendix B), which is also the table order of the pickle.
 '''
 
+import re
+
 import numpy as np
 
 FARADAY = 9.64853e4         # constants.py:12
@@ -88,6 +90,7 @@ _q10_mrg_mp = 2.2**((CELSIUS - 20.0) / 10)    # mrg.py:59-63
 _q10_mrg_h = 2.9**((CELSIUS - 20.0) / 10)
 _q10_mrg_s = 3.0**((CELSIUS - 36.0) / 10)
 _q10_su = 3**((CELSIUS - 30.0) / 10)          # sundt.py:60-62
+_q10_hh = 3**((CELSIUS - 6.3) / 10.)          # hh.py:31,46-48
 _T = CELSIUS + CELSIUS_2_KELVIN               # pneuron.py:28
 
 NEURON_SPECS = {
@@ -172,9 +175,45 @@ NEURON_SPECS = {
         Rate('alphal', 'q10BG * (0.001 * exp(-(2.) * 1. * xl)) * 1e3'),
         Rate('betal', 'q10BG * (0.001 * exp((2.) * (1 - 1.) * xl)) * 1e3'),
     ]),
+    # ---- giant squid axon segment (hh.py:13-75) ----
+    'HHseg': dict(Cm0=1e-2, Vm0=-65.0, consts=dict(q10=_q10_hh), kin=[
+        Rate('alpham', 'q10 * 0.1 * vtrap(-(Vm + 40), 10) * 1e3'),
+        Rate('betam', 'q10 * 4 * exp(-(Vm + 65) / 18) * 1e3'),
+        Rate('alphah', 'q10 * 0.07 * exp(-(Vm + 65) / 20) * 1e3'),
+        Rate('betah', 'q10 * 1.0 / (exp(-(Vm + 35) / 10) + 1) * 1e3'),
+        Rate('alphan', 'q10 * 0.01 * vtrap(-(Vm + 55), 10) * 1e3'),
+        Rate('betan', 'q10 * 0.125 * exp(-(Vm + 65) / 80) * 1e3'),
+    ]),
+    # ---- leech touch cell (leech.py:15-160): xinf = 1 / (1 + exp((V - half) / slope))^power,
+    # ---- taux = (tauMax - tauMin) / (1 + exp((V - half) / slope)) + tauMin, or constant ----
+    'LeechT': dict(Cm0=1e-2, Vm0=-53.58, consts={}, kin=[
+        Gate('m', '1 / (1 + exp((Vm - (-35.0)) / (-5.0)))', '0.1e-3'),
+        Gate('h', '1 / (hb * hb)', '(14.0e-3 - 0.2e-3) / (1 + exp((Vm - (-36.0)) / 3.5)) + 0.2e-3',
+             pre=['hb = 1 + exp((Vm - (-50.0)) / 9.0)']),
+        Gate('n', '1 / (1 + exp((Vm - (-22.0)) / (-9.0)))',
+             '(6.0e-3 - 1.0e-3) / (1 + exp((Vm - (-10.0)) / 10.0)) + 1.0e-3'),
+        Gate('s', '1 / (1 + exp((Vm - (-10.0)) / (-2.8)))', '0.6e-3'),
+    ]),
+    # ---- leech pressure cell (leech.py:236-300, 369-400) ----
+    'LeechP': dict(Cm0=1e-2, Vm0=-48.865, consts={}, kin=[
+        Rate('alpham', '-0.03 * (Vm + 28) / (exp(-(Vm + 28) / 15) - 1) * 1e3'),
+        Rate('betam', '2.7 * exp(-(Vm + 53) / 18) * 1e3'),
+        Rate('alphah', '0.045 * exp(-(Vm + 58) / 18) * 1e3'),
+        Rate('betah', '0.72 / (exp(-(Vm + 23) / 14) + 1) * 1e3'),
+        Rate('alphan', '-0.024 * (Vm - 17) / (exp(-(Vm - 17) / 8) - 1) * 1e3'),
+        Rate('betan', '0.2 * exp(-(Vm + 48) / 35) * 1e3'),
+        Rate('alphas', '-1.5 * (Vm - 20) / (exp(-(Vm - 20) / 5) - 1) * 1e3'),
+        Rate('betas', '1.5 * exp(-(Vm + 25) / 10) * 1e3'),
+    ]),
+    # ---- template neuron (template.py:13-70): the Pospischil m, h, n gates ----
+    'template': dict(Cm0=1e-2, Vm0=-71.9, consts=dict(VT=-56.2), kin=_pospischil_mhn()),
+    # ---- passive membrane (pas.py:16-110): no gate, only V is tabulated; Cm0 and the resting potential
+    # ---- (= ELeak) are set per instance by `passiveNeuron`, these are the defaults of pas.py:103-107 ----
+    'pas': dict(Cm0=1e-2, Vm0=-70., consts={}, kin=[]),
 }
 
-NEURON_ORDER = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg']
+NEURON_ORDER = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg',
+                'HHseg', 'LeechT', 'LeechP', 'template', 'pas']
 MAX_RATES = 18
 
 
@@ -195,7 +234,7 @@ class PointNeuron:
     def __init__(self, name):
         if name not in NEURON_SPECS:
             raise ValueError(f'"{name}" neuron not found. Implemented neurons are: ' +
-                             ', '.join(f'"{k}"' for k in NEURON_ORDER))
+                             ', '.join(f'"{k}"' for k in NEURON_ORDER if k != 'pas'))
         spec = NEURON_SPECS[name]
         self.name = name
         self.Cm0 = spec['Cm0']
@@ -229,6 +268,97 @@ class PointNeuron:
         return eval_mean_rates(self, np.asarray(Vm, dtype=np.float64))
 
 
+_PAS_PATTERN = re.compile(r'pas_Cm0_{0}uF_cm2_gLeak_{0}S_m2_ELeak_{0}mV'.format(r'([+-]?\d+\.?\d*)'))
+
+
+class PassiveNeuron(PointNeuron):
+    ''' Point neuron with only a passive (leakage) current (pas.py:23-100): no gating variable, so
+        its lookup holds the effective potential only.  Name and lookup name follow pas.py:47-63. '''
+
+    def __init__(self, Cm0, gLeak, ELeak):
+        super().__init__('pas')
+        self.Cm0, self.gLeak, self.ELeak = Cm0, gLeak, ELeak
+        self.Vm0 = ELeak                                   # pas.py:74-76
+
+    def pdict(self):
+        return {'Cm0': f'{self.Cm0 * 1e2:.1f} uF/cm2', 'gLeak': f'{self.gLeak:.1f} S/m2',
+                'ELeak': f'{self.ELeak:.1f} mV'}
+
+    @staticmethod
+    def code(pdict):
+        pdict = {k: v.replace(' ', '').replace('/', '_') for k, v in pdict.items()}
+        return 'pas_' + '_'.join(f'{k}_{v}' for k, v in pdict.items())
+
+    @property
+    def name(self):
+        return self.code(self.pdict())
+
+    @name.setter
+    def name(self, value):
+        pass
+
+    @property
+    def lookup_name(self):
+        pdict = self.pdict()
+        del pdict['gLeak']
+        return self.code(pdict)
+
+    @property
+    def is_passive(self):
+        return True
+
+    def __repr__(self):
+        return 'PassiveNeuron(' + ', '.join(f'{k} = {v}' for k, v in self.pdict().items()) + ')'
+
+    def __eq__(self, other):
+        return isinstance(other, PassiveNeuron) and self.name == other.name
+
+
+def passiveNeuron(*args):
+    ''' Passive neuron from (Cm0 F/m2, gLeak S/m2, ELeak mV) or from its name (pas.py:16-22). '''
+    if len(args) == 1:
+        Cm0, gLeak, ELeak = [float(x) for x in re.findall(_PAS_PATTERN, args[0])[0]]
+        Cm0 *= 1e-2
+    else:
+        Cm0, gLeak, ELeak = args
+    return PassiveNeuron(Cm0, gLeak, ELeak)
+
+
+def getDefaultPassiveNeuron():
+    ''' pas.py:103-107 '''
+    return passiveNeuron(1e-2, 1e2, -70)
+
+
 def getPointNeuron(name):
-    ''' Same lookup-by-name as PySONIC/neurons/__init__.py:24-44. '''
+    ''' Same lookup-by-name as PySONIC/neurons/__init__.py:24-44 (passive neurons by their
+        parameter-carrying name, pas.py:16-19). '''
+    if isinstance(name, str) and name.startswith('pas_'):
+        return passiveNeuron(name)
     return PointNeuron(name)
+
+
+def check_foreign_neuron(pneuron, mine, Vm=(-120., -71.9, -40., 0., 35.)):
+    ''' A point-neuron object that is not this package's own (e.g. a reference PySONIC instance) is
+        mapped onto the built-in kinetics by its name: make sure that it IS that neuron -- same resting
+        capacitance and potential, same ordered rate names, and, when it can evaluate its rate
+        functions (`effRates()`, translators.py:396-419), the same values -- instead of silently
+        ignoring modified parameters. '''
+    for attr in ('Cm0', 'Vm0'):
+        if hasattr(pneuron, attr) and not np.isclose(getattr(pneuron, attr), getattr(mine, attr), rtol=1e-12, atol=0):
+            raise ValueError(f'{pneuron}: {attr} = {getattr(pneuron, attr)} differs from the built-in '
+                             f'"{mine.name}" kinetics ({getattr(mine, attr)})')
+    rates = getattr(pneuron, 'rates', None)
+    if rates is not None and list(rates) != list(mine.rates):
+        raise ValueError(f'{pneuron}: rate constants {list(rates)} differ from the built-in "{mine.name}" '
+                         f'kinetics ({mine.rates})')
+    eff = getattr(pneuron, 'effRates', None)
+    if callable(eff) and mine.rates:
+        from . import _lib
+        if _lib.device_count() > 0:
+            theirs = eff()
+            ours = _lib.eval_rates(mine, np.array(Vm))
+            for k in mine.rates:
+                ref = np.array([float(theirs[k](np.float64(v))) for v in Vm])
+                if not np.allclose(ours[k], ref, rtol=1e-9, atol=0, equal_nan=True):
+                    raise ValueError(f'{pneuron}: rate "{k}" differs from the built-in "{mine.name}" kinetics')
+    return mine

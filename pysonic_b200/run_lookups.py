@@ -14,7 +14,7 @@ from . import _lib
 from .constants import DQ_LOOKUP
 from .lookups import Lookup
 from .nbls import NeuronalBilayerSonophore, as_point_neuron, check_charges
-from .neurons import getPointNeuron
+from .neurons import getDefaultPassiveNeuron, getPointNeuron
 from .parallel import (dist_info, env_world, finalize, init_from_env, predicted_log_cost, run_sharded,
                        trajectory_groups)
 
@@ -128,7 +128,9 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
     logger.log(loglevel, 'Starting lookup batch for %s neuron: %d points x %d fs', pneuron.name,
                na * nf * nA * nQ, nfs)
 
-    bls_params = [NeuronalBilayerSonophore(float(a), pneuron).abi_params() for a in refs['a']]
+    # a passive neuron is simulated on the sonophore of the default passive neuron (run_lookups.py:141-145)
+    bls_neuron = getDefaultPassiveNeuron() if pneuron.is_passive else pneuron
+    bls_params = [NeuronalBilayerSonophore(float(a), bls_neuron).abi_params() for a in refs['a']]
     if mpi:
         init_from_env()          # under torchrun: bind to the rank's GPU, join the process group
     rank, world, local_rank = dist_info()

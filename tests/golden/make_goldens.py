@@ -173,10 +173,51 @@ def gen_points():
     print('points.json:', len(recs), 'points')
 
 
+def gen_points2():
+    ''' Known-answer points for the remaining @addSonicFeatures neurons (hh.py, leech.py, template.py) and
+        the passive membrane (pas.py; run_lookups.py:141-145 simulates it on the default passive neuron). '''
+    from PySONIC.neurons import getDefaultPassiveNeuron
+    jobs = []
+    for name, Q in [('HHseg', -65e-5), ('LeechT', -53.58e-5), ('LeechP', -48.865e-5), ('template', -71.9e-5)]:
+        jobs += [(name, 32e-9, 500e3, 100e3, Q, [1.0]), (name, 32e-9, 2e6, 400e3, 30e-5, [0.5, 1.0]),
+                 (name, 32e-9, 100e3, 20e3, -80e-5, [1.0])]
+    recs = pmap(jobs)
+    for scale in (1.0 + 4.440892098500626e-16, 1.0 - 4.440892098500626e-16):
+        pert = pmap([(j[0], j[1], j[2], j[3] * scale, j[4], j[5]) for j in jobs])
+        for r, q in zip(recs, pert):
+            dev = 0.0
+            for ev, evq in zip(r['effvars'], q['effvars']):
+                for k in ev:
+                    d = abs(ev[k] - evq[k])
+                    if d >= 1e-9:
+                        dev = max(dev, d / abs(ev[k]))
+            r['self_noise'] = max(r.get('self_noise', 0.0), dev)
+    # passive membrane: only V
+    pas = getDefaultPassiveNeuron()
+    nb = NeuronalBilayerSonophore(32e-9, pas)
+    prec = []
+    for f, A, Q, fs in [(500e3, 100e3, -70e-5, [1.0]), (1e6, 300e3, 20e-5, [0.3, 1.0]), (20e3, 50e3, -100e-5, [1.0])]:
+        _counters['ncycles'] = 0
+        ev, _ = nb.computeEffVars(AcousticDrive(f, A), np.array(fs), Q)
+        prec.append({'neuron': pas.name, 'lookup_name': pas.lookup_name, 'a': 32e-9, 'f': f, 'A': A, 'Q': Q, 'fs': fs,
+                     'ncycles': _counters['ncycles'], 'effvars': [{k: float(v) for k, v in e.items()} for e in ev],
+                     'self_noise': 0.0, 'Qbounds': list(map(float, pas.Qbounds)), 'Qm0': pas.Qm0,
+                     'fname': nb.getLookupFileName()})
+    consts = {}
+    for name in ['HHseg', 'LeechT', 'LeechP', 'template']:
+        nb = _nbls(name, 32e-9)
+        consts[f'{name}@32nm'] = {'Delta': nb.Delta, 'Cm0': nb.Cm0, 'Qm0': nb.Qm0, 'LJ': nb.LJ_approx,
+                                  'Qbounds': list(map(float, nb.pneuron.Qbounds)), 'rates': list(nb.pneuron.rates)}
+    with open(os.path.join(HERE, 'points_r02.json'), 'w') as fh:
+        json.dump({'points': recs, 'passive': prec, 'consts': consts}, fh, indent=1)
+    print('points_r02.json:', len(recs), '+', len(prec), 'points')
+
+
 def gen_rates():
     ''' Every tabulated rate function of every supported neuron on a Vm sweep that includes
         the singular / branch points (vtrap 0/0, tauu branch). '''
-    names = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg']
+    names = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg',
+             'HHseg', 'LeechT', 'LeechP', 'template']
     Vm = np.concatenate([np.linspace(-450., 350., 401),
                          np.array([-43.2, -16.2, -41.2, -48.0, -57.0, -35.0, -61.0, -27.0,
                                    -21.4, -25.7, -114.0, -80.0, -73.0, -87.0 + 7.0, -83.0,
@@ -349,7 +390,7 @@ def gen_noise():
 
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
-    todo = {'points': gen_points, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
+    todo = {'points': gen_points, 'points2': gen_points2, 'rates': gen_rates, 'c1': gen_c1, 'neurons': gen_neurons,
             'c2sub': gen_c2sub, 'cm': gen_cm,
             'noise4': lambda: [fn(sc, tg) for fn in (gen_neurons, gen_cortical)
                                for sc, tg in ((1.0 + 8.881784197001252e-16, '_ulp_up2'),
@@ -363,5 +404,5 @@ if __name__ == '__main__':
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4', 'c2big', 'neurons_big')):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4', 'c2big', 'neurons_big', 'points2')):
             fn()

@@ -720,3 +720,54 @@ def test_computePMparams_for_radii_outside_the_table(gpu):
     nbls = ps.NeuronalBilayerSonophore(50e-9, ps.getPointNeuron('RE'))
     ev, _ = nbls.computeEffVars(ps.AcousticDrive(700e3, 80e3), 1.0, -89.5e-5)
     assert np.isfinite(ev[0]['V']) and ev[0]['V'] < 0
+
+
+def test_known_answer_points_of_the_remaining_neurons(gpu):
+    ''' HHseg, LeechT, LeechP, template (hh.py, leech.py, template.py) and the passive membrane
+        (pas.py, run_lookups.py:141-145): reference known-answer points. '''
+    import json
+    ps = _ps()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'points_r02.json')) as fh:
+        g = json.load(fh)
+    for p in g['points']:
+        nbls = ps.NeuronalBilayerSonophore(p['a'], ps.getPointNeuron(p['neuron']))
+        out, ncyc, status, _, _, _ = nbls.effvars_batch(p['f'], p['A'], p['Q'], p['fs'])
+        tol = max(RTOL, 5.0 * p['self_noise'])
+        assert abs(int(ncyc[0]) - p['ncycles']) <= (0 if p['self_noise'] < 1e-5 else 1), p
+        keys = ['V'] + nbls.pneuron.rates
+        for j, ref in enumerate(p['effvars']):
+            assert list(ref.keys()) == keys
+            for i, k in enumerate(keys):
+                assert rel_err(out[i, 0, j], ref[k]) <= tol, (p['neuron'], p['f'], p['A'], p['Q'], k)
+    pas = ps.getDefaultPassiveNeuron()
+    for p in g['passive']:
+        lkp, info = ps.computeAStimLookup(pas, np.array([p['a']]), np.array([p['f']]), np.array([p['A']]),
+                                          np.array(p['fs']), np.array([p['Q']]), return_info=True, loglevel=10)
+        assert list(lkp.tables.keys()) == ['V', 'tcomp']
+        for j, ref in enumerate(p['effvars']):
+            assert list(ref.keys()) == ['V']
+            assert rel_err(lkp['V'][0, 0, 0, 0, j], ref['V']) <= RTOL
+        assert int(info['ncycles'].ravel()[0]) == p['ncycles']
+
+
+def test_foreign_neuron_rates_are_checked_on_the_device(gpu):
+    ''' as_point_neuron on an object that can evaluate its own rate functions (the reference's
+        `effRates()`): a neuron that only shares the name of a built-in one is refused. '''
+    ps = _ps()
+    from pysonic_b200.nbls import as_point_neuron
+
+    class Tweaked:
+        name, Cm0, Vm0 = 'HHseg', 1e-2, -65.0
+        rates = ['alpham', 'betam', 'alphah', 'betah', 'alphan', 'betan']
+
+        def __init__(self, scale):
+            self.scale = scale
+
+        def effRates(self):
+            base = ps.getPointNeuron('HHseg')
+            return {k: (lambda v, k=k: gpu.eval_rates(base, np.array([v]))[k][0] * (self.scale if k == 'betan' else 1.0))
+                    for k in self.rates}
+
+    assert as_point_neuron(Tweaked(1.0)).name == 'HHseg'
+    with pytest.raises(ValueError, match='betan'):
+        as_point_neuron(Tweaked(1.5))

@@ -34,7 +34,7 @@ def test_neuron_descriptors_match_reference(points_golden):
 
 
 def test_rates_golden_neurons_all_declared(rates_golden):
-    assert set(rates_golden['neurons']) == set(NEURON_ORDER)
+    assert set(rates_golden['neurons']) == set(NEURON_ORDER) - {'pas'}      # the passive membrane has no gate
     for name, rec in rates_golden['neurons'].items():
         assert spec_rate_names(name) == rec['rates']
         assert NEURON_SPECS[name]['Cm0'] == rec['Cm0'] and NEURON_SPECS[name]['Vm0'] == rec['Vm0']
@@ -329,3 +329,66 @@ def test_lj_fit_host_logic_with_cpu_quadrature():
         for k in ('x0', 'C', 'nrep', 'nattr'):
             assert abs(LJ[k] - rec[k]) <= tol * abs(rec[k]), (rec['a'], k, LJ[k], rec[k])
         assert std_err < 5e3
+
+
+# ---------------------------------------------------------------------------------------------
+# remaining @addSonicFeatures neurons, passive membrane factory, foreign PointNeuron objects
+# ---------------------------------------------------------------------------------------------
+def _points_r02():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'points_r02.json')) as fh:
+        return json.load(fh)
+
+
+def test_new_neuron_descriptors_match_reference():
+    g = _points_r02()
+    for key, c in g['consts'].items():
+        name = key.split('@')[0]
+        pn = ps.getPointNeuron(name)
+        assert pn.rates == c['rates'] and pn.Cm0 == c['Cm0'] and pn.Qm0 == c['Qm0']
+        np.testing.assert_array_equal(pn.Qbounds, c['Qbounds'])
+        nbls = ps.NeuronalBilayerSonophore(32e-9, pn)
+        assert nbls.Delta == c['Delta'] and nbls.LJ_approx == c['LJ']
+    with pytest.raises(ValueError, match='not found'):
+        ps.getPointNeuron('LeechR')          # not a SONIC-enabled neuron in the reference either
+
+
+def test_passive_neuron_factory_mirrors_reference():
+    ''' pas.py:16-107: name and lookup name carry the parameters, the resting potential is ELeak,
+        there is no rate constant; run_lookups.py:141-145 files its lookup under `lookup_name`. '''
+    rec = _points_r02()['passive'][0]
+    pas = ps.getDefaultPassiveNeuron()
+    assert pas.is_passive and pas.rates == [] and not ps.getPointNeuron('RS').is_passive
+    assert pas.name == rec['neuron'] and pas.lookup_name == rec['lookup_name']
+    assert pas.Qm0 == pytest.approx(rec['Qm0'], rel=1e-15)
+    np.testing.assert_allclose(pas.Qbounds, rec['Qbounds'], rtol=1e-15)
+    assert ps.NeuronalBilayerSonophore(32e-9, pas).getLookupFileName() == rec['fname']
+    # by name (getPointNeuron on a passive-neuron code) and with other parameters
+    again = ps.getPointNeuron(pas.name)
+    assert again == pas and again.Cm0 == 1e-2 and again.gLeak == 100.0 and again.Vm0 == -70.0
+    p2 = ps.passiveNeuron(2e-2, 50., -65.)
+    assert p2.name == 'pas_Cm0_2.0uF_cm2_gLeak_50.0S_m2_ELeak_-65.0mV' and p2.Qm0 == pytest.approx(2e-2 * -65e-3)
+
+
+def test_foreign_point_neuron_is_verified_not_trusted_by_name():
+    ''' An object that merely carries a known name (a reference PointNeuron instance, say) must be
+        that neuron: modified parameters raise instead of being ignored. '''
+    from pysonic_b200.nbls import as_point_neuron
+
+    class Foreign:
+        name, Cm0, Vm0 = 'RS', 1e-2, -71.9
+        rates = ['alpham', 'betam', 'alphah', 'betah', 'alphan', 'betan', 'alphap', 'betap']
+
+    assert as_point_neuron(Foreign()) == ps.getPointNeuron('RS')
+    f = Foreign()
+    f.Vm0 = -65.0
+    with pytest.raises(ValueError, match='Vm0'):
+        as_point_neuron(f)
+    f = Foreign()
+    f.Cm0 = 2e-2
+    with pytest.raises(ValueError, match='Cm0'):
+        as_point_neuron(f)
+    f = Foreign()
+    f.rates = f.rates[:6]
+    with pytest.raises(ValueError, match='rate constants'):
+        as_point_neuron(f)
