@@ -447,6 +447,48 @@ def _su():
     ]
 
 
+def _hh():
+    ''' hh.py:31,46-75 '''
+    q10 = 3**((36.0 - 6.3) / 10.)
+    return [
+        ('alpham', lambda V: q10 * 0.1 * vtrap(-(V + 40), 10) * 1e3),
+        ('betam', lambda V: q10 * 4 * np.exp(-(V + 65) / 18) * 1e3),
+        ('alphah', lambda V: q10 * 0.07 * np.exp(-(V + 65) / 20) * 1e3),
+        ('betah', lambda V: q10 * 1.0 / (np.exp(-(V + 35) / 10) + 1) * 1e3),
+        ('alphan', lambda V: q10 * 0.01 * vtrap(-(V + 55), 10) * 1e3),
+        ('betan', lambda V: q10 * 0.125 * np.exp(-(V + 65) / 80) * 1e3),
+    ]
+
+
+def _leech_t():
+    ''' leech.py:74-147: xinf = 1 / (1 + exp((V - half) / slope))^power; taux constant or sigmoidal '''
+    xinf = lambda half, slope, power: (lambda V: 1 / (1 + np.exp((V - half) / slope))**power)
+    taux = lambda half, slope, tmax, tmin: (lambda V: (tmax - tmin) / (1 + np.exp((V - half) / slope)) + tmin)
+    const = lambda c: (lambda V: c + 0 * V)
+    out = []
+    for key, inf, tau in [('m', xinf(-35.0, -5.0, 1), const(0.1e-3)),
+                          ('h', xinf(-50.0, 9.0, 2), taux(-36.0, 3.5, 14.0e-3, 0.2e-3)),
+                          ('n', xinf(-22.0, -9.0, 1), taux(-10.0, 10.0, 6.0e-3, 1.0e-3)),
+                          ('s', xinf(-10.0, -2.8, 1), const(0.6e-3))]:
+        a, b = _ab_from_inf_tau(inf, tau)
+        out += [('alpha' + key, a), ('beta' + key, b)]
+    return out
+
+
+def _leech_p():
+    ''' leech.py:258-296 '''
+    return [
+        ('alpham', lambda V: -0.03 * (V + 28) / (np.exp(- (V + 28) / 15) - 1) * 1e3),
+        ('betam', lambda V: 2.7 * np.exp(-(V + 53) / 18) * 1e3),
+        ('alphah', lambda V: 0.045 * np.exp(-(V + 58) / 18) * 1e3),
+        ('betah', lambda V: 0.72 / (np.exp(-(V + 23) / 14) + 1) * 1e3),
+        ('alphan', lambda V: -0.024 * (V - 17) / (np.exp(-(V - 17) / 8) - 1) * 1e3),
+        ('betan', lambda V: 0.2 * np.exp(-(V + 48) / 35) * 1e3),
+        ('alphas', lambda V: -1.5 * (V - 20) / (np.exp(-(V - 20) / 5) - 1) * 1e3),
+        ('betas', lambda V: 1.5 * np.exp(-(V + 25) / 10) * 1e3),
+    ]
+
+
 NEURONS = {
     # name: (Cm0 [F/m2], Vm0 [mV], ordered rate list)
     'RS': (1e-2, -71.9, _pospischil_mhn(-56.2) + _cortical_p(0.608)),
@@ -460,6 +502,11 @@ NEURONS = {
     'SWnode': (2.5e-2, -80.0, _sw()),
     'MRGnode': (2e-2, -80., _mrg()),
     'SUseg': (1e-2, -60., _su()),
+    'HHseg': (1e-2, -65.0, _hh()),
+    'LeechT': (1e-2, -53.58, _leech_t()),
+    'LeechP': (1e-2, -48.865, _leech_p()),
+    'template': (1e-2, -71.9, _pospischil_mhn(-56.2)),
+    'pas': (1e-2, -70., []),          # passive membrane (pas.py:103-107): no gate
 }
 
 

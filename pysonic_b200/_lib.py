@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsonic_b200.so')
+# (development: PYSONIC_B200_LIB selects another build of the same library, e.g. a kernel variant to time)
+LIB_PATH = os.environ.get('PYSONIC_B200_LIB') or os.path.join(_HERE, 'libsonic_b200.so')
 
 
 class SonicError(RuntimeError):

@@ -38,6 +38,10 @@
 #endif
 #define SONIC_HIST_STRIDE SONIC_BLOCK   /* per-lane indexed storage interleaved across the block */
 /* tick time of a warp with k busy lanes relative to a lone lane: 1 + GAIN (1 - exp(-(k - 1) / KDEC)) (measured) */
+/* warps with at most this many busy lanes run the nested tick (0 = never) */
+#ifndef SONIC_LONE_MAXK
+#define SONIC_LONE_MAXK 1
+#endif
 #ifndef SONIC_SCHED_GAIN
 #define SONIC_SCHED_GAIN 1.55
 #endif
@@ -104,6 +108,7 @@ struct SonicJob {
     int* block_smid;           // [blocks]: SM each block ran on (placement probe / diagnostics)
     long long n;
     int probe;                 // 1 = record the block placement and return
+    int lone_maxk;             // warps with at most this many busy lanes run the nested tick
 };
 
 __constant__ SonicTables c_tables;
@@ -127,6 +132,9 @@ __global__ void __launch_bounds__(128) sonic_z0_kernel(SonicJob job) {
     job.z0[i] = ok ? z0 : nan("");
 }
 
+// OVT: points carry charge overtones (a separate instantiation keeps the Fourier-series charge code out of
+// the instruction stream of the common case; the integrator's hot loop competes for the SM's instruction cache)
+template <bool OVT>
 __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integrate_kernel(SonicJob job) {
     if (threadIdx.x == 0) {
         unsigned smid;
@@ -191,8 +199,8 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
             if (q < (unsigned long long)job.n) {
                 pt = job.order[q];
                 const double f = job.f[pt];
-                sonic_point_init(p, job.radii[job.ia[pt]], f, job.A[pt], job.Q[pt], job.nov,
-                                 job.nov ? job.ov + (size_t)pt * 2 * job.nov : nullptr);
+                sonic_point_init(p, job.radii[job.ia[pt]], f, job.A[pt], job.Q[pt], OVT ? job.nov : 0,
+                                 OVT ? job.ov + (size_t)pt * 2 * job.nov : nullptr);
                 period = 1.0 / f;
                 sink.zbuf = job.zbuf + pt * SONIC_NPC;
                 const double z0 = job.z0[pt];
@@ -224,10 +232,25 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
         }
         // tick until a lane of this warp finishes its point (the set of busy lanes is fixed till then)
         bool fin = false;
+#if SONIC_LONE_MAXK > 0
+        if (__popc(wmask) <= job.lone_maxk) {
+            // few busy lanes (the long chains the host hands out to sparsely populated warps): nothing to
+            // share between lanes, each follows its own path through the nested tick
+            do {
+                if (active) {
+                    double fv[3];
+                    if (OVT) sonic_update_charge(p, s.tn);
+                    if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
+                    sonic_tick_lone(s, H, &tab, p, sink, period, fv);
+                    fin = s.phase == PH_DONE;
+                }
+            } while (!__any_sync(0xffffffffu, fin));
+        } else
+#endif
         do {
             if (active) {
                 double fv[3];
-                if (p.nov) sonic_update_charge(p, s.tn);
+                if (OVT) sonic_update_charge(p, s.tn);
                 if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
                 sonic_tick(s, H, &tab, p, sink, period, fv, wmask);
                 fin = s.phase == PH_DONE;
@@ -499,11 +522,16 @@ static int device_info(int device, DeviceInfo* out) {
         CUDA_TRY(cudaSetDevice(device));
         CUDA_TRY(cudaMemcpyToSymbol(c_tables, &host_tables(), sizeof(SonicTables)));
         CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
-        CUDA_TRY(cudaFuncSetAttribute(sonic_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(sonic_integrate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SONIC_HIST_BYTES));
-        int bps = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sonic_integrate_kernel, SONIC_BLOCK,
+        CUDA_TRY(cudaFuncSetAttribute(sonic_integrate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)SONIC_HIST_BYTES));
+        int bps = 0, bps_ov = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sonic_integrate_kernel<false>, SONIC_BLOCK,
                                                                SONIC_HIST_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_ov, sonic_integrate_kernel<true>, SONIC_BLOCK,
+                                                               SONIC_HIST_BYTES));
+        if (bps_ov < bps) bps = bps_ov;
         d.blocks_per_sm = bps < 1 ? 1 : bps;
         d.ready = true;
     }
@@ -1027,7 +1055,8 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         zj.radii = p->d_radii; zj.ia = p->d_ia; zj.f = p->d_f; zj.A = p->d_A; zj.Q = p->d_Q;
         zj.z0 = p->d_z0; zj.n = p->n; zj.ov = p->d_ov; zj.nov = p->nov;
         sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(zj);
-        sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
+        if (p->nov) sonic_integrate_kernel<true><<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
+        else sonic_integrate_kernel<false><<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(probe);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(smid.data(), p->d_block_smid, blocks * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         CUDA_TRY(cudaStreamSynchronize(p->stream));
@@ -1234,6 +1263,10 @@ int sonic_plan_launch(SonicPlan* p) {
     job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
     job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
     job.block_smid = p->d_block_smid; job.probe = 0;
+    // the nested tick only when no warp of the plan ever holds more than one point (small grids, single
+    // points): on an SM whose warps run both drivers the two instruction streams evict each other
+    job.lone_maxk = (SONIC_LONE_MAXK > 0 && p->lanes_per_warp == 1) ? SONIC_LONE_MAXK : 0;
+    if (const char* e = getenv("SONIC_LONE_MAXK")) job.lone_maxk = atoi(e);
     cudaEvent_t* ev = p->ws->ev;
     p->result_on_host = false;
     CUDA_TRY(cudaMemcpyAsync(p->d_counter, p->d_counter0, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, p->stream));
@@ -1241,7 +1274,8 @@ int sonic_plan_launch(SonicPlan* p) {
     CUDA_TRY(cudaEventRecord(ev[0], p->stream));
     sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(ev[1], p->stream));
-    sonic_integrate_kernel<<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(job);
+    if (p->nov) sonic_integrate_kernel<true><<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(job);
+    else sonic_integrate_kernel<false><<<p->grid, SONIC_BLOCK, SONIC_HIST_BYTES, p->stream>>>(job);
     CUDA_TRY(cudaEventRecord(ev[2], p->stream));
     for (int k = 0; k < (int)p->neurons.size(); k++) {
         cudaError_t e = cudaSuccess;

@@ -43,8 +43,11 @@
 #define SONIC_DIVC(x, c) ((x) * (1.0 / (c)))
 #endif
 // Stage boundary of the tick: re-converge the lanes of the warp that entered the tick (they
-// took different branches inside the previous stage) so that the next stage is executed once,
-// by all lanes that need it, instead of once per divergent path.
+// took different branches inside the previous stages) so that the next stage is executed once,
+// by all lanes that need it, instead of once per divergent path.  Placed in front of the pieces that
+// lanes reach from different paths -- the corrector, the history rescale, the prediction; a boundary
+// in front of every stage costs more instructions than it saves (measured, profiles/README.md), none
+// at all lets the lanes drift apart (C2: 1.78 s instead of 1.42 s).
 #if defined(__CUDA_ARCH__)
 #define SONIC_STAGE_SYNC(mask) __syncwarp(mask)
 #else
@@ -1110,9 +1113,389 @@ SONIC_HD double sonic_jac_incr(const SonicLane& s, double yj, double wj) {
     return fmax(1.4901161193847656e-08 * fabs(yj), sonic_div(s.jac_r0, wj));
 }
 
+// ---------------------------------------------------------------------------------------
+// Pieces of a tick.  They are shared by the two drivers below -- the staged one (lanes of a warp in
+// different phases execute every piece they have in common together) and the nested one (a lane that
+// is alone in its warp follows its own path with as few branches as possible) -- so that both perform
+// exactly the same arithmetic in the same order: a point gets the same bits from either.
+// ---------------------------------------------------------------------------------------
+
+// P = I - h el0 J must be re-evaluated (finite-difference Jacobian).  Only the Z column needs a full
+// right-hand side (the next tick, at y + r_Z e_Z); the U and ng columns are exact differences of the
+// terms that depend on them (sonic_rhs_diff_cols).  savf holds f(y) already.
+SONIC_HD void sonic_jac_setup(SonicLane& s) {
+    s.nje++;
+    s.ierpj = 0;
+    s.jcur = 1;
+    const double fac = sonic_mnorm(s.savf, s.ewt);
+    double r0 = 1000.0 * fabs(s.h) * SONIC_UROUND * 3.0 * fac;
+    if (r0 == 0.0) r0 = 1.0;
+    s.jac_r0 = r0;
+    s.yj_save = s.y[1];
+    s.y[1] = s.yj_save + sonic_jac_incr(s, s.yj_save, s.ewt[1]);
+    s.phase = PH_JAC;
+}
+
+// f = RHS at (U, Z + r_Z, ng): assemble and factorise the iteration matrix.  Returns false when it
+// is singular (a corrector failure with a current Jacobian).  LSODA counts three evaluations per
+// Jacobian.
+SONIC_HD bool sonic_jac_consume(SonicLane& s, const SonicHist& H, const SonicPoint& p, const double f[3]) {
+    s.nfe += 2;
+    const double hl0 = s.h * s.el0;
+    {
+        const double rr = sonic_jac_incr(s, s.yj_save, s.ewt[1]);
+        const double fac = -sonic_div(hl0, rr);
+        H.wm(0 + 3) = (f[0] - s.savf[0]) * fac;
+        H.wm(1 + 3) = (f[1] - s.savf[1]) * fac;
+        H.wm(2 + 3) = (f[2] - s.savf[2]) * fac;
+        s.y[1] = s.yj_save;
+    }
+    {
+        const double r0u = sonic_jac_incr(s, s.y[0], s.ewt[0]);
+        const double r2n = sonic_jac_incr(s, s.y[2], s.ewt[2]);
+        // the increments actually applied by y_j + r in floating point
+        const double rU = (s.y[0] + r0u) - s.y[0];
+        const double rN = (s.y[2] + r2n) - s.y[2];
+        double d0[3], d2[3];
+        sonic_rhs_diff_cols(p, s.y, rU, rN, d0, d2);
+        const double fac0 = -sonic_div(hl0, r0u);
+        const double fac2 = -sonic_div(hl0, r2n);
+        H.wm(0) = d0[0] * fac0; H.wm(1) = d0[1] * fac0; H.wm(2) = d0[2] * fac0;
+        H.wm(6) = d2[0] * fac2; H.wm(7) = d2[1] * fac2; H.wm(8) = d2[2] * fac2;
+    }
+    // norm of the Jacobian (matrix norm consistent with the weighted max-norm)
+    double an = 0.0;
+    double rew[3];
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) rew[jj] = sonic_rcp(s.ewt[jj]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double sm = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++)
+            sm += SONIC_QUOT(fabs(H.wm(i + 3 * jj)), s.ewt[jj], rew[jj]);
+        an = fmax(an, sm * s.ewt[i]);
+    }
+    s.pdnorm = sonic_div(an, fabs(hl0));
+    H.wm(0) += 1.0; H.wm(4) += 1.0; H.wm(8) += 1.0;
+    const int info = sonic_lu3(H, &s.ipvt);
+    s.ipup = 0;
+    s.rc = 1.0;
+    s.nslp = s.nst;
+    s.crate = 0.7;
+    if (info != 0) {
+        s.ierpj = 1;
+        return false;
+    }
+    s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
+    return true;
+}
+
+// Fresh problem (one per cycle): initial step size and history from f(t0, y0).
+SONIC_HD void sonic_init_problem(SonicLane& s, const SonicHist& H, const double f[3]) {
+    H.yh(0, 0) = s.y[0]; H.yh(0, 1) = s.y[1]; H.yh(0, 2) = s.y[2];
+    s.nst = 0; s.nslast = 0; s.mused = 0; s.miter = 0;
+    s.meth = 1; s.jstart = 0; s.nq = 1;
+    sonic_ewset(s, H);
+    const double tdist = fabs(s.tout - s.tn);
+    const double w0 = fmax(fabs(s.tn), fabs(s.tout));
+    double tol = SONIC_RTOL;
+    tol = fmax(tol, 100.0 * SONIC_UROUND);
+    tol = fmin(tol, 0.001);
+    double sum = sonic_mnorm(f, s.ewt);
+    sum = 1.0 / (tol * w0 * w0) + tol * sum * sum;
+    double h0 = 1.0 / sqrt(sum);
+    h0 = fmin(h0, tdist);
+    s.h = h0;   // tout > t always
+    H.yh(1, 0) = h0 * f[0]; H.yh(1, 1) = h0 * f[1]; H.yh(1, 2) = h0 * f[2];
+}
+
+// Order reset after 3+ error-test failures, from f(t_n, y_n).
+SONIC_HD void sonic_reset_order(SonicLane& s, const SonicHist& H, const SonicTables* T, const double f[3]) {
+    H.yh(1, 0) = s.h * f[0]; H.yh(1, 1) = s.h * f[1]; H.yh(1, 2) = s.h * f[2];
+    s.ipup = s.miter;
+    s.ialth = 5;
+    if (s.nq != 1) {
+        s.nq = 1;
+        sonic_set_order(s, T);
+    }
+}
+
+// Corrector update with savf (functional iteration or chord / Newton) and convergence test.
+// Outcome: converged, failed (corr_failed), or one more iterate (phase = PH_CORR_ITER).
+SONIC_HD void sonic_corrector(SonicLane& s, const SonicHist& H, const SonicTables* T, bool& converged,
+                              bool& corr_failed) {
+    const double el1 = SONIC_EL(s, T, 0);
+    const double yh00 = H.yh(0, 0), yh01 = H.yh(0, 1), yh02 = H.yh(0, 2);
+    const double yh10 = H.yh(1, 0), yh11 = H.yh(1, 1), yh12 = H.yh(1, 2);
+    if (s.miter == 0) {
+        s.savf[0] = s.h * s.savf[0] - yh10;
+        s.savf[1] = s.h * s.savf[1] - yh11;
+        s.savf[2] = s.h * s.savf[2] - yh12;
+        s.del = sonic_mnorm3(s.savf[0] - s.acor[0], s.savf[1] - s.acor[1],
+                             s.savf[2] - s.acor[2], s.ewt);
+        s.y[0] = yh00 + el1 * s.savf[0];
+        s.y[1] = yh01 + el1 * s.savf[1];
+        s.y[2] = yh02 + el1 * s.savf[2];
+        s.acor[0] = s.savf[0]; s.acor[1] = s.savf[1]; s.acor[2] = s.savf[2];
+    } else {
+        double d[3];
+        d[0] = s.h * s.savf[0] - (yh10 + s.acor[0]);
+        d[1] = s.h * s.savf[1] - (yh11 + s.acor[1]);
+        d[2] = s.h * s.savf[2] - (yh12 + s.acor[2]);
+        sonic_lusolve3(H, s.ipvt, d);
+        s.del = sonic_mnorm(d, s.ewt);
+        s.acor[0] += d[0]; s.acor[1] += d[1]; s.acor[2] += d[2];
+        s.y[0] = yh00 + el1 * s.acor[0];
+        s.y[1] = yh01 + el1 * s.acor[1];
+        s.y[2] = yh02 + el1 * s.acor[2];
+    }
+    // convergence test
+    if (s.del <= 100.0 * s.pnorm * SONIC_UROUND) {
+        converged = true;
+    } else if (!(s.m == 0 && s.meth == 1)) {
+        if (s.m != 0) {
+            double rm = 1024.0;
+            if (s.del <= 1024.0 * s.delp) rm = sonic_div(s.del, s.delp);
+            s.rate = fmax(s.rate, rm);
+            s.crate = fmax(0.2 * s.crate, rm);
+        }
+#ifdef SONIC_CHECK_TABLES
+        if (fabs(SONIC_RCON(s, T) * (SONIC_TESCO(s, T, 1) * s.conit) - 1.0) > 1e-12) abort();
+#endif
+        const double dcon = SONIC_QUOT(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit, SONIC_RCON(s, T));
+        if (dcon <= 1.0) {
+            s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));
+            if (s.pdest != 0.0) s.pdlast = s.pdest;
+            converged = true;
+        }
+    }
+    if (!converged) {
+        s.m++;
+        if (s.m == 3 || (s.m >= 2 && s.del > 2.0 * s.delp)) {
+            corr_failed = true;
+        } else {
+            s.delp = s.del;
+            s.phase = PH_CORR_ITER;   // next RHS at (tn, y)
+        }
+    }
+}
+
+// Local error estimate of a converged step; returns true if the error test fails.
+SONIC_HD bool sonic_error_test(SonicLane& s, const SonicTables* T) {
+    s.jcur = 0;
+    s.dsm = SONIC_QUOT((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), SONIC_TESCO(s, T, 1), SONIC_RTESCO(s, T, 1));
+    return s.dsm > 1.0;
+}
+
+// Corrector failure without a current Jacobian: same step again with a fresh one.
+SONIC_HD void sonic_retry_with_jacobian(SonicLane& s, const SonicHist& H) {
+    s.ipup = s.miter;
+    s.m = 0;
+    s.rate = 0.0;
+    s.del = 0.0;
+    s.y[0] = H.yh(0, 0);
+    s.y[1] = H.yh(0, 1);
+    s.y[2] = H.yh(0, 2);
+    s.phase = PH_CORR_FIRST;
+}
+
+// Retraction after a failed corrector iteration (cf = true) or a failed error test: restore tn and
+// the history, then decide how to go on.  Outcome through the flags: predict again with the filed
+// step-size change, order/step selection (sel_mode = 2), order reset (phase = PH_RESET), or failure.
+SONIC_HD void sonic_retract(SonicLane& s, const SonicHist& H, bool cf, bool& do_predict, int& sel_mode,
+                            SonicRescaleReq& rq) {
+    s.tn = s.told;
+    sonic_pascal(s, H, -1.0);
+    s.rmax = 2.0;
+    if (cf) {
+        s.ncf++;
+        if (fabs(s.h) <= 0.0 || s.ncf == 10) {
+            sonic_fail(s, SONIC_ST_STEPFAIL);
+        } else {
+            s.ipup = s.miter;
+            rq.pending = true; rq.rh = 0.25; rq.rmax10 = false;
+            do_predict = true;
+        }
+    } else {
+        // error test failed: shrink the step (and maybe the order)
+        s.kflag--;
+        if (fabs(s.h) <= 0.0 || s.kflag == -10) {
+            sonic_fail(s, SONIC_ST_STEPFAIL);
+        } else if (s.kflag <= -3) {
+            // 3+ failures: restart at order 1 with a 10x smaller step
+            s.h *= 0.1;
+            s.y[0] = H.yh(0, 0);
+            s.y[1] = H.yh(0, 1);
+            s.y[2] = H.yh(0, 2);
+            s.phase = PH_RESET;
+        } else {
+            sel_mode = 2;
+        }
+    }
+}
+
+// The step is accepted: update the history.  Returns true when a method switch has to be considered.
+SONIC_HD bool sonic_accept(SonicLane& s, const SonicHist& H, const SonicTables* T) {
+    s.kflag = 0;
+    s.nst++;
+    s.nsteps++;
+#ifdef SONIC_TRACE
+    s.hu = s.h;
+    s.nqu = s.nq;
+#endif
+    s.mused = s.meth;
+    {
+        const double* el = &SONIC_EL(s, T, 0);
+#pragma unroll
+        for (int j = 0; j <= 5; j++) {
+            if (j <= s.nq) {
+                const double e = el[j];
+                H.yh(j, 0) += e * s.acor[0];
+                H.yh(j, 1) += e * s.acor[1];
+                H.yh(j, 2) += e * s.acor[2];
+            }
+        }
+#pragma unroll 1
+        for (int j = 6; j <= s.nq; j++) {
+            const double e = el[j];
+            H.yh(j, 0) += e * s.acor[0];
+            H.yh(j, 1) += e * s.acor[1];
+            H.yh(j, 2) += e * s.acor[2];
+        }
+    }
+    s.icount--;
+    return s.icount < 0;
+}
+
+// Step/order bookkeeping after a success without method switch: every ialth steps prepare the
+// order/step selection (sel_mode = 1, candidate for an order increase in sel_rhup).
+SONIC_HD void sonic_after_accept(SonicLane& s, const SonicHist& H, const SonicTables* T, int& sel_mode,
+                                 double& sel_rhup) {
+    const int l = s.nq + 1;
+    const int lmax = SONIC_LMAX(s);
+    s.ialth--;
+    if (s.ialth == 0) {
+        if (l != lmax) {
+            const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
+                                            s.acor[1] - H.yh(lmax - 1, 1),
+                                            s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
+            const double dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
+            const double exup = T->rk[l + 1];
+            sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
+        }
+        sel_mode = 1;
+    } else if (s.ialth <= 1 && l != lmax) {
+        H.yh(lmax - 1, 0) = s.acor[0];
+        H.yh(lmax - 1, 1) = s.acor[1];
+        H.yh(lmax - 1, 2) = s.acor[2];
+    }
+}
+
+// Emit every output sample reached by the accepted step; end-of-cycle logic (solvers.py:317-365).
+// begin_mode: 2 = go on with the next step, 0 = a new cycle (or nothing) has been set up.
+SONIC_HD void sonic_emit(SonicLane& s, const SonicHist& H, const SonicSink& sink, double period, int& begin_mode) {
+    begin_mode = 2;
+    while ((s.tn - s.tout) * s.h >= 0.0) {
+        double yo[3];
+        sonic_interp(s, H, s.tout, yo);
+        if (s.cyc >= 1) {
+            const double dz = yo[1] - s.prev_z;
+            const double dn = yo[2] - s.prev_ng;
+            H.at(SONIC_H_SSQZ) += dz * dz;
+            H.at(SONIC_H_SSQN) += dn * dn;
+            H.at(SONIC_H_MINZ) = fmin(H.at(SONIC_H_MINZ), yo[1]);
+            H.at(SONIC_H_MAXZ) = fmax(H.at(SONIC_H_MAXZ), yo[1]);
+            H.at(SONIC_H_MINN) = fmin(H.at(SONIC_H_MINN), yo[2]);
+            H.at(SONIC_H_MAXN) = fmax(H.at(SONIC_H_MAXN), yo[2]);
+        }
+        sink.zbuf[s.kout] = yo[1];
+        sink.ngbuf[s.kout] = yo[2];
+        if (s.kout == SONIC_NOUT) {
+            // end of cycle
+            bool stop = false;
+            if (s.cyc >= 1) {
+                const double rz = sqrt(H.at(SONIC_H_SSQZ) / (double)SONIC_NOUT) /
+                                  (H.at(SONIC_H_MAXZ) - H.at(SONIC_H_MINZ));
+                const double rn = sqrt(H.at(SONIC_H_SSQN) / (double)SONIC_NOUT) /
+                                  (H.at(SONIC_H_MAXN) - H.at(SONIC_H_MINN));
+                const bool stable = (rz < SONIC_CONV_THR) && (rn < SONIC_CONV_THR);
+                if (stable) stop = true;
+                else if (s.cyc >= SONIC_NCYC_CAP - 1) {
+                    stop = true;
+                    s.status |= SONIC_ST_NOCONV;
+                }
+            }
+            s.cyc++;
+            begin_mode = 0;
+            if (stop) {
+                s.phase = PH_DONE;
+            } else {
+                sink.zbuf[0] = yo[1];
+                sink.ngbuf[0] = yo[2];
+                sonic_cycle_begin(s, H, sink, s.tstop, period, yo);
+            }
+            break;
+        }
+        s.kout++;
+        s.tout = sonic_tout_at(s, s.kout);
+        s.nslast = s.nst;
+        if (s.cyc >= 1) {
+            s.prev_z = sink.zbuf[s.kout];
+            s.prev_ng = sink.ngbuf[s.kout];
+        }
+    }
+}
+
+// Preliminaries of the next step (begin_mode 1 = first step of a problem, 2 = after a success).
+// Returns true when the step can be predicted.
+SONIC_HD bool sonic_begin_step(SonicLane& s, const SonicHist& H, const SonicTables* T, int begin_mode) {
+    if (begin_mode == 2) {
+        if (s.nst - s.nslast >= SONIC_MXSTEP) {
+            sonic_fail(s, SONIC_ST_MXSTEP);
+            return false;
+        }
+        sonic_ewset(s, H);
+    }
+    // (the "too much accuracy requested" test of the original driver cannot fire here:
+    //  |y| * ewt <= 1 / rtol = 6.7e7, far below 1 / uround)
+    s.kflag = 0;
+    s.told = s.tn;
+    s.ncf = 0;
+    s.ierpj = 0;
+    s.jcur = 0;
+    s.delp = 0.0;
+    if (s.jstart == 0) {
+        s.nq = 1;
+        s.ialth = 2;
+        s.rmax = 10000.0;
+        s.rc = 0.0;
+        s.el0 = 1.0;
+        s.crate = 0.7;
+        s.nslp = 0;
+        s.ipup = s.miter;
+        s.icount = 20;
+        s.irflag = 0;
+        s.pdest = 0.0;
+        s.pdlast = 0.0;
+        s.tab_meth = 1;
+        sonic_set_order(s, T);
+    } else if (s.jstart == -1) {
+        s.ipup = s.miter;
+        if (s.ialth == 1) s.ialth = 2;
+        if (s.meth != s.mused) {
+            s.tab_meth = s.meth;
+            s.ialth = s.nq + 1;
+            sonic_set_order(s, T);
+        }
+    }
+    s.jstart = 1;
+    return true;
+}
+
 // One tick: consume the RHS value `f` evaluated at (s.tn, s.y) and advance the lane to its
-// next evaluation point.  The body is a sequence of stages guarded by flags, so that lanes of
-// a warp that are in different phases still share every stage they have in common.
+// next evaluation point.  Staged driver: the body is a sequence of stages guarded by flags, so that
+// lanes of a warp that are in different phases still share every stage they have in common.
 SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
                          const SonicPoint& p, const SonicSink& sink, double period,
                          const double f[3], unsigned wmask) {
@@ -1127,191 +1510,35 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     if (s.phase == PH_CORR_FIRST || s.phase == PH_CORR_ITER) {
         s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
         if (s.phase == PH_CORR_FIRST && s.ipup > 0) {
-            // P = I - h el0 J must be re-evaluated: finite-difference Jacobian.  Only the Z column
-            // needs a full right-hand side (the next tick, at y + r_Z e_Z); the U and ng columns
-            // are exact differences of the terms that depend on them (sonic_rhs_diff_cols).
-            s.nje++;
-            s.ierpj = 0;
-            s.jcur = 1;
-            const double fac = sonic_mnorm(s.savf, s.ewt);
-            double r0 = 1000.0 * fabs(s.h) * SONIC_UROUND * 3.0 * fac;
-            if (r0 == 0.0) r0 = 1.0;
-            s.jac_r0 = r0;
-            s.yj_save = s.y[1];
-            s.y[1] = s.yj_save + sonic_jac_incr(s, s.yj_save, s.ewt[1]);
-            s.phase = PH_JAC;
+            sonic_jac_setup(s);
         } else {
             if (s.phase == PH_CORR_FIRST) s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
             do_corr = true;
         }
     } else if (s.phase == PH_JAC) {
-        // f = RHS at (U, Z + r_Z, ng); LSODA counts three evaluations per Jacobian
-        s.nfe += 2;
-        const double hl0 = s.h * s.el0;
-        {
-            const double rr = sonic_jac_incr(s, s.yj_save, s.ewt[1]);
-            const double fac = -sonic_div(hl0, rr);
-            H.wm(0 + 3) = (f[0] - s.savf[0]) * fac;
-            H.wm(1 + 3) = (f[1] - s.savf[1]) * fac;
-            H.wm(2 + 3) = (f[2] - s.savf[2]) * fac;
-            s.y[1] = s.yj_save;
-        }
-        {
-            const double r0u = sonic_jac_incr(s, s.y[0], s.ewt[0]);
-            const double r2n = sonic_jac_incr(s, s.y[2], s.ewt[2]);
-            // the increments actually applied by y_j + r in floating point
-            const double rU = (s.y[0] + r0u) - s.y[0];
-            const double rN = (s.y[2] + r2n) - s.y[2];
-            double d0[3], d2[3];
-            sonic_rhs_diff_cols(p, s.y, rU, rN, d0, d2);
-            const double fac0 = -sonic_div(hl0, r0u);
-            const double fac2 = -sonic_div(hl0, r2n);
-            H.wm(0) = d0[0] * fac0; H.wm(1) = d0[1] * fac0; H.wm(2) = d0[2] * fac0;
-            H.wm(6) = d2[0] * fac2; H.wm(7) = d2[1] * fac2; H.wm(8) = d2[2] * fac2;
-        }
-        {
-            // norm of the Jacobian (matrix norm consistent with the weighted max-norm)
-            double an = 0.0;
-            double rew[3];
-#pragma unroll
-            for (int jj = 0; jj < 3; jj++) rew[jj] = sonic_rcp(s.ewt[jj]);
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                double sm = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < 3; jj++)
-                    sm += SONIC_QUOT(fabs(H.wm(i + 3 * jj)), s.ewt[jj], rew[jj]);
-                an = fmax(an, sm * s.ewt[i]);
-            }
-            s.pdnorm = sonic_div(an, fabs(hl0));
-            H.wm(0) += 1.0; H.wm(4) += 1.0; H.wm(8) += 1.0;
-            const int info = sonic_lu3(H, &s.ipvt);
-            s.ipup = 0;
-            s.rc = 1.0;
-            s.nslp = s.nst;
-            s.crate = 0.7;
-            if (info != 0) {
-                // singular iteration matrix: corrector failure with a current Jacobian
-                s.ierpj = 1;
-                corr_failed = true;
-            } else {
-                s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
-                do_corr = true;
-            }
-        }
+        if (sonic_jac_consume(s, H, p, f)) do_corr = true;
+        else corr_failed = true;
     } else if (s.phase == PH_INIT) {
-        // fresh problem (one per cycle): initial step size, history, first step
-        H.yh(0, 0) = s.y[0]; H.yh(0, 1) = s.y[1]; H.yh(0, 2) = s.y[2];
-        s.nst = 0; s.nslast = 0; s.mused = 0; s.miter = 0;
-        s.meth = 1; s.jstart = 0; s.nq = 1;
-        sonic_ewset(s, H);
-        const double tdist = fabs(s.tout - s.tn);
-        const double w0 = fmax(fabs(s.tn), fabs(s.tout));
-        double tol = SONIC_RTOL;
-        tol = fmax(tol, 100.0 * SONIC_UROUND);
-        tol = fmin(tol, 0.001);
-        double sum = sonic_mnorm(f, s.ewt);
-        sum = 1.0 / (tol * w0 * w0) + tol * sum * sum;
-        double h0 = 1.0 / sqrt(sum);
-        h0 = fmin(h0, tdist);
-        s.h = h0;   // tout > t always
-        H.yh(1, 0) = h0 * f[0]; H.yh(1, 1) = h0 * f[1]; H.yh(1, 2) = h0 * f[2];
+        sonic_init_problem(s, H, f);
         begin_mode = 1;
     } else if (s.phase == PH_RESET) {
-        H.yh(1, 0) = s.h * f[0]; H.yh(1, 1) = s.h * f[1]; H.yh(1, 2) = s.h * f[2];
-        s.ipup = s.miter;
-        s.ialth = 5;
-        if (s.nq != 1) {
-            s.nq = 1;
-            sonic_set_order(s, T);
-        }
+        sonic_reset_order(s, H, T, f);
         do_predict = true;
     }
 
     SONIC_STAGE_SYNC(wmask);
     // ---- stage B: corrector update (functional iteration or chord/Newton) ---------------
     bool converged = false;
-    if (do_corr) {
-        const double el1 = SONIC_EL(s, T, 0);
-        const double yh00 = H.yh(0, 0), yh01 = H.yh(0, 1), yh02 = H.yh(0, 2);
-        const double yh10 = H.yh(1, 0), yh11 = H.yh(1, 1), yh12 = H.yh(1, 2);
-        if (s.miter == 0) {
-            s.savf[0] = s.h * s.savf[0] - yh10;
-            s.savf[1] = s.h * s.savf[1] - yh11;
-            s.savf[2] = s.h * s.savf[2] - yh12;
-            s.del = sonic_mnorm3(s.savf[0] - s.acor[0], s.savf[1] - s.acor[1],
-                                 s.savf[2] - s.acor[2], s.ewt);
-            s.y[0] = yh00 + el1 * s.savf[0];
-            s.y[1] = yh01 + el1 * s.savf[1];
-            s.y[2] = yh02 + el1 * s.savf[2];
-            s.acor[0] = s.savf[0]; s.acor[1] = s.savf[1]; s.acor[2] = s.savf[2];
-        } else {
-            double d[3];
-            d[0] = s.h * s.savf[0] - (yh10 + s.acor[0]);
-            d[1] = s.h * s.savf[1] - (yh11 + s.acor[1]);
-            d[2] = s.h * s.savf[2] - (yh12 + s.acor[2]);
-            sonic_lusolve3(H, s.ipvt, d);
-            s.del = sonic_mnorm(d, s.ewt);
-            s.acor[0] += d[0]; s.acor[1] += d[1]; s.acor[2] += d[2];
-            s.y[0] = yh00 + el1 * s.acor[0];
-            s.y[1] = yh01 + el1 * s.acor[1];
-            s.y[2] = yh02 + el1 * s.acor[2];
-        }
-        // convergence test
-        if (s.del <= 100.0 * s.pnorm * SONIC_UROUND) {
-            converged = true;
-        } else if (!(s.m == 0 && s.meth == 1)) {
-            if (s.m != 0) {
-                double rm = 1024.0;
-                if (s.del <= 1024.0 * s.delp) rm = sonic_div(s.del, s.delp);
-                s.rate = fmax(s.rate, rm);
-                s.crate = fmax(0.2 * s.crate, rm);
-            }
-#ifdef SONIC_CHECK_TABLES
-            if (fabs(SONIC_RCON(s, T) * (SONIC_TESCO(s, T, 1) * s.conit) - 1.0) > 1e-12) abort();
-#endif
-            const double dcon = SONIC_QUOT(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit, SONIC_RCON(s, T));
-            if (dcon <= 1.0) {
-                s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));
-                if (s.pdest != 0.0) s.pdlast = s.pdest;
-                converged = true;
-            }
-        }
-        if (!converged) {
-            s.m++;
-            if (s.m == 3 || (s.m >= 2 && s.del > 2.0 * s.delp)) {
-                corr_failed = true;
-            } else {
-                s.delp = s.del;
-                s.phase = PH_CORR_ITER;   // next RHS at (tn, y)
-            }
-        }
-    }
+    if (do_corr) sonic_corrector(s, H, T, converged, corr_failed);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage R: retraction after a failed corrector iteration or a failed error test ---
     // (both restore tn and the history before shrinking the step)
     bool err_failed = false;
-    if (converged) {
-        s.jcur = 0;
-        s.dsm = SONIC_QUOT((s.m == 0) ? s.del : sonic_mnorm(s.acor, s.ewt), SONIC_TESCO(s, T, 1), SONIC_RTESCO(s, T, 1));
-        err_failed = s.dsm > 1.0;
-    }
+    if (converged) err_failed = sonic_error_test(s, T);
     bool cf_retract = false;
     if (corr_failed) {
-        if (s.miter != 0 && s.jcur != 1) {
-            // retry with a fresh Jacobian at the predicted state
-            s.ipup = s.miter;
-            s.m = 0;
-            s.rate = 0.0;
-            s.del = 0.0;
-            s.y[0] = H.yh(0, 0);
-            s.y[1] = H.yh(0, 1);
-            s.y[2] = H.yh(0, 2);
-            s.phase = PH_CORR_FIRST;
-        } else {
-            cf_retract = true;
-        }
+        if (s.miter != 0 && s.jcur != 1) sonic_retry_with_jacobian(s, H);
+        else cf_retract = true;
     }
     int sel_mode = 0;          // 1 = order/step selection after a success, 2 = after a failure
     double sel_rhup = 0.0;
@@ -1319,102 +1546,20 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     ctx.rhsm0 = ctx.lds = NAN;
     SonicRescaleReq rq;
     rq.pending = false; rq.rmax10 = false; rq.rh = 1.0;
-    if (cf_retract || err_failed) {
-        s.tn = s.told;
-        sonic_pascal(s, H, -1.0);
-        s.rmax = 2.0;
-        if (cf_retract) {
-            s.ncf++;
-            if (fabs(s.h) <= 0.0 || s.ncf == 10) {
-                sonic_fail(s, SONIC_ST_STEPFAIL);
-            } else {
-                s.ipup = s.miter;
-                rq.pending = true; rq.rh = 0.25; rq.rmax10 = false;
-                do_predict = true;
-            }
-        } else {
-            // error test failed: shrink the step (and maybe the order)
-            s.kflag--;
-            if (fabs(s.h) <= 0.0 || s.kflag == -10) {
-                sonic_fail(s, SONIC_ST_STEPFAIL);
-            } else if (s.kflag <= -3) {
-                // 3+ failures: restart at order 1 with a 10x smaller step
-                s.h *= 0.1;
-                s.y[0] = H.yh(0, 0);
-                s.y[1] = H.yh(0, 1);
-                s.y[2] = H.yh(0, 2);
-                s.phase = PH_RESET;
-            } else {
-                sel_mode = 2;
-            }
-        }
-    }
+    if (cf_retract || err_failed) sonic_retract(s, H, cf_retract, do_predict, sel_mode, rq);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage C: the step is accepted: update the history -------------------------------
     const bool accepted = converged && !err_failed;
     bool do_mswitch = false;
-    if (accepted) {
-        s.kflag = 0;
-        s.nst++;
-        s.nsteps++;
-#ifdef SONIC_TRACE
-        s.hu = s.h;
-        s.nqu = s.nq;
-#endif
-        s.mused = s.meth;
-        {
-            const double* el = &SONIC_EL(s, T, 0);
-#pragma unroll
-            for (int j = 0; j <= 5; j++) {
-                if (j <= s.nq) {
-                    const double e = el[j];
-                    H.yh(j, 0) += e * s.acor[0];
-                    H.yh(j, 1) += e * s.acor[1];
-                    H.yh(j, 2) += e * s.acor[2];
-                }
-            }
-#pragma unroll 1
-            for (int j = 6; j <= s.nq; j++) {
-                const double e = el[j];
-                H.yh(j, 0) += e * s.acor[0];
-                H.yh(j, 1) += e * s.acor[1];
-                H.yh(j, 2) += e * s.acor[2];
-            }
-        }
-        s.icount--;
-        do_mswitch = s.icount < 0;
-    }
+    if (accepted) do_mswitch = sonic_accept(s, H, T);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage C2: consider switching between the Adams and BDF families -----------------
     bool switched = false;
     if (do_mswitch) switched = sonic_method_switch(s, H, T, &ctx, rq);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage C3: step/order bookkeeping after a success ---------------------------------
-    if (accepted && !switched) {
-        const int l = s.nq + 1;
-        const int lmax = SONIC_LMAX(s);
-        s.ialth--;
-        if (s.ialth == 0) {
-            if (l != lmax) {
-                const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
-                                                s.acor[1] - H.yh(lmax - 1, 1),
-                                                s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
-                const double dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
-                const double exup = T->rk[l + 1];
-                sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
-            }
-            sel_mode = 1;
-        } else if (s.ialth <= 1 && l != lmax) {
-            H.yh(lmax - 1, 0) = s.acor[0];
-            H.yh(lmax - 1, 1) = s.acor[1];
-            H.yh(lmax - 1, 2) = s.acor[2];
-        }
-    }
+    if (accepted && !switched) sonic_after_accept(s, H, T, sel_mode, sel_rhup);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage C4: order and step-size selection (after a success or a failed error test) -
     if (sel_mode != 0) {
         const bool redo = sonic_select(s, H, T, sel_rhup, sel_mode == 2 ? 2 : 0, &ctx, rq);
@@ -1430,114 +1575,94 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         if (rq.rmax10) s.rmax = 10.0;
     }
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage D: emit every output sample reached; end-of-cycle logic ------------------
-    if (accepted) {
-        begin_mode = 2;
-        while ((s.tn - s.tout) * s.h >= 0.0) {
-            double yo[3];
-            sonic_interp(s, H, s.tout, yo);
-            if (s.cyc >= 1) {
-                const double dz = yo[1] - s.prev_z;
-                const double dn = yo[2] - s.prev_ng;
-                H.at(SONIC_H_SSQZ) += dz * dz;
-                H.at(SONIC_H_SSQN) += dn * dn;
-                H.at(SONIC_H_MINZ) = fmin(H.at(SONIC_H_MINZ), yo[1]);
-                H.at(SONIC_H_MAXZ) = fmax(H.at(SONIC_H_MAXZ), yo[1]);
-                H.at(SONIC_H_MINN) = fmin(H.at(SONIC_H_MINN), yo[2]);
-                H.at(SONIC_H_MAXN) = fmax(H.at(SONIC_H_MAXN), yo[2]);
-            }
-            sink.zbuf[s.kout] = yo[1];
-            sink.ngbuf[s.kout] = yo[2];
-            if (s.kout == SONIC_NOUT) {
-                // end of cycle (solvers.py:317-365)
-                bool stop = false;
-                if (s.cyc >= 1) {
-                    const double rz = sqrt(H.at(SONIC_H_SSQZ) / (double)SONIC_NOUT) /
-                                      (H.at(SONIC_H_MAXZ) - H.at(SONIC_H_MINZ));
-                    const double rn = sqrt(H.at(SONIC_H_SSQN) / (double)SONIC_NOUT) /
-                                      (H.at(SONIC_H_MAXN) - H.at(SONIC_H_MINN));
-                    const bool stable = (rz < SONIC_CONV_THR) && (rn < SONIC_CONV_THR);
-                    if (stable) stop = true;
-                    else if (s.cyc >= SONIC_NCYC_CAP - 1) {
-                        stop = true;
-                        s.status |= SONIC_ST_NOCONV;
-                    }
-                }
-                s.cyc++;
-                begin_mode = 0;
-                if (stop) {
-                    s.phase = PH_DONE;
-                } else {
-                    sink.zbuf[0] = yo[1];
-                    sink.ngbuf[0] = yo[2];
-                    sonic_cycle_begin(s, H, sink, s.tstop, period, yo);
-                }
-                break;
-            }
-            s.kout++;
-            s.tout = sonic_tout_at(s, s.kout);
-            s.nslast = s.nst;
-            if (s.cyc >= 1) {
-                s.prev_z = sink.zbuf[s.kout];
-                s.prev_ng = sink.ngbuf[s.kout];
-            }
-        }
-    }
+    if (accepted) sonic_emit(s, H, sink, period, begin_mode);
 
-    SONIC_STAGE_SYNC(wmask);
     // ---- stage E: preliminaries of the next step ------------------------------------------
     if (begin_mode != 0) {
-        bool ok = true;
-        if (begin_mode == 2) {
-            if (s.nst - s.nslast >= SONIC_MXSTEP) {
-                sonic_fail(s, SONIC_ST_MXSTEP);
-                ok = false;
-            } else {
-                sonic_ewset(s, H);
-            }
-        }
-        // (the "too much accuracy requested" test of the original driver cannot fire here:
-        //  |y| * ewt <= 1 / rtol = 6.7e7, far below 1 / uround)
-        if (ok) {
-            s.kflag = 0;
-            s.told = s.tn;
-            s.ncf = 0;
-            s.ierpj = 0;
-            s.jcur = 0;
-            s.delp = 0.0;
-            if (s.jstart == 0) {
-                s.nq = 1;
-                s.ialth = 2;
-                s.rmax = 10000.0;
-                s.rc = 0.0;
-                s.el0 = 1.0;
-                s.crate = 0.7;
-                s.nslp = 0;
-                s.ipup = s.miter;
-                s.icount = 20;
-                s.irflag = 0;
-                s.pdest = 0.0;
-                s.pdlast = 0.0;
-                s.tab_meth = 1;
-                sonic_set_order(s, T);
-            } else if (s.jstart == -1) {
-                s.ipup = s.miter;
-                if (s.ialth == 1) s.ialth = 2;
-                if (s.meth != s.mused) {
-                    s.tab_meth = s.meth;
-                    s.ialth = s.nq + 1;
-                    sonic_set_order(s, T);
-                }
-            }
-            s.jstart = 1;
-            do_predict = true;
-        }
+        if (sonic_begin_step(s, H, T, begin_mode)) do_predict = true;
     }
 
     SONIC_STAGE_SYNC(wmask);
     // ---- stage F: prediction (start or redo a step) ---------------------------------------
     if (do_predict) sonic_predict(s, H);
+}
+
+// Nested driver of the same tick, for a lane that is alone in its warp: no stage flags, every lane
+// state follows its own path and leaves as soon as its next evaluation point is set.  Same pieces,
+// same order, same arithmetic as sonic_tick.
+SONIC_HD void sonic_tick_lone(SonicLane& s, const SonicHist& H, const SonicTables* T,
+                              const SonicPoint& p, const SonicSink& sink, double period,
+                              const double f[3]) {
+    s.nfe++;
+    bool converged = false, corr_failed = false, do_predict = false;
+    int sel_mode = 0;
+    SonicRescaleReq rq;
+    rq.pending = false; rq.rmax10 = false; rq.rh = 1.0;
+    const int phase = s.phase;
+    if (phase == PH_CORR_FIRST || phase == PH_CORR_ITER) {
+        s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
+        if (phase == PH_CORR_FIRST) {
+            if (s.ipup > 0) {
+                sonic_jac_setup(s);
+                return;
+            }
+            s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
+        }
+        sonic_corrector(s, H, T, converged, corr_failed);
+    } else if (phase == PH_JAC) {
+        if (sonic_jac_consume(s, H, p, f)) sonic_corrector(s, H, T, converged, corr_failed);
+        else corr_failed = true;
+    } else if (phase == PH_INIT) {
+        sonic_init_problem(s, H, f);
+        if (sonic_begin_step(s, H, T, 1)) sonic_predict(s, H);
+        return;
+    } else {      // PH_RESET
+        sonic_reset_order(s, H, T, f);
+        sonic_predict(s, H);
+        return;
+    }
+    if (!converged && !corr_failed) return;           // one more corrector iterate at (tn, y)
+    SonicStepCtx ctx;
+    ctx.rhsm0 = ctx.lds = NAN;
+    bool failed = corr_failed;                        // a path that retracts the step
+    if (corr_failed) {
+        if (s.miter != 0 && s.jcur != 1) {
+            sonic_retry_with_jacobian(s, H);
+            return;
+        }
+    } else {
+        failed = sonic_error_test(s, T);
+    }
+    if (failed) {
+        sonic_retract(s, H, corr_failed, do_predict, sel_mode, rq);
+        if (sel_mode == 2) {
+            sonic_select(s, H, T, 0.0, 2, &ctx, rq);
+            do_predict = true;
+        }
+        if (rq.pending) {
+            sonic_rescale(s, H, T, rq.rh);
+            if (rq.rmax10) s.rmax = 10.0;
+        }
+        if (do_predict) sonic_predict(s, H);
+        return;
+    }
+    // accepted step
+    bool switched = false;
+    if (sonic_accept(s, H, T)) switched = sonic_method_switch(s, H, T, &ctx, rq);
+    if (!switched) {
+        double sel_rhup = 0.0;
+        sonic_after_accept(s, H, T, sel_mode, sel_rhup);
+        if (sel_mode != 0) sonic_select(s, H, T, sel_rhup, 0, &ctx, rq);
+    }
+    if (s.meth != s.mused) s.jstart = -1;             // method switch: reload coefficients
+    if (rq.pending) {
+        sonic_rescale(s, H, T, rq.rh);
+        if (rq.rmax10) s.rmax = 10.0;
+    }
+    int begin_mode;
+    sonic_emit(s, H, sink, period, begin_mode);
+    if (begin_mode != 0 && sonic_begin_step(s, H, T, begin_mode)) sonic_predict(s, H);
 }
 
 // Start a lane on its grid point with a precomputed initial deflection.

@@ -13,10 +13,13 @@
 static SonicTables g_tab;
 static int g_tab_ready = 0;
 
+static int g_driver = 0;   // 0 = staged tick (sonic_tick), 1 = nested tick of a lone lane (sonic_tick_lone)
 static double* g_steplog = 0;
 static long g_steplog_max = 0, g_steplog_n = 0;
 
 extern "C" {
+
+void hostsim_set_driver(int d) { g_driver = d; }
 
 // optional per-step log: rows of 8 doubles [cycle, nst, tn, hu, h_next, nqu*10+mused, nfe, nq*10+meth]
 void hostsim_set_steplog(double* buf, long max_rows) {
@@ -62,7 +65,8 @@ long hostsim_point_ov(const double* bls, double f, double A, double Q, int nov, 
         double fv[3];
         if (p.nov) sonic_update_charge(p, s.tn);
         if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-        sonic_tick(s, H, &g_tab, p, sink, period, fv, 0u);
+        if (g_driver == 1) sonic_tick_lone(s, H, &g_tab, p, sink, period, fv);
+        else sonic_tick(s, H, &g_tab, p, sink, period, fv, 0u);
         nticks++;
         if (g_steplog && s.nsteps != last_nsteps && g_steplog_n < g_steplog_max) {
             double* r = g_steplog + 8 * g_steplog_n++;
