@@ -43,10 +43,10 @@
 #define SONIC_LONE_MAXK 1
 #endif
 #ifndef SONIC_SCHED_GAIN
-#define SONIC_SCHED_GAIN 1.55
+#define SONIC_SCHED_GAIN 1.8
 #endif
 #ifndef SONIC_SCHED_KDEC
-#define SONIC_SCHED_KDEC 2.5
+#define SONIC_SCHED_KDEC 4.0
 #endif
 
 #include "../../include/sonic_b200.h"
@@ -108,7 +108,7 @@ struct SonicJob {
     int* block_smid;           // [blocks]: SM each block ran on (placement probe / diagnostics)
     long long n;
     int probe;                 // 1 = record the block placement and return
-    int lone_maxk;             // warps with at most this many busy lanes run the nested tick
+    const int* block_nested;   // [blocks]: 1 = this block runs the nested tick (plans whose warps hold one point at a time)
 };
 
 __constant__ SonicTables c_tables;
@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     // expensive points out first, to warps that keep only `cap` lanes busy while those points
     // run; once they are done the warp works at full width on whatever is left in the queue.
     const int gwarp = (int)(slot >> 5);
+#if SONIC_LONE_MAXK > 0
+    const bool nested = job.block_nested[blockIdx.x] != 0;
+#endif
     int cap = job.warp_cap[gwarp];
     long long q_init = (lane < cap) ? (long long)job.warp_first[gwarp] + lane : -1;
     bool exhausted = false;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
         // tick until a lane of this warp finishes its point (the set of busy lanes is fixed till then)
         bool fin = false;
 #if SONIC_LONE_MAXK > 0
-        if (__popc(wmask) <= job.lone_maxk) {
+        if (nested) {
             // few busy lanes (the long chains the host hands out to sparsely populated warps): nothing to
             // share between lanes, each follows its own path through the nested tick
             do {
@@ -697,6 +700,7 @@ struct SonicPlan {
     SonicBls* d_radii = nullptr;
     int *d_order = nullptr, *d_ia = nullptr, *d_ia_out = nullptr, *d_umap = nullptr, *d_sel = nullptr;
     int *d_warp_first = nullptr, *d_warp_cap = nullptr, *d_block_smid = nullptr, *d_ncycles = nullptr;
+    int* d_block_nested = nullptr;
     double *d_f = nullptr, *d_A = nullptr, *d_Q = nullptr, *d_fs = nullptr, *d_ov = nullptr, *d_Qout = nullptr;
     double *d_z0 = nullptr, *d_zbuf = nullptr, *d_ngbuf = nullptr, *d_tpoint = nullptr, *d_out = nullptr;
     unsigned *d_status = nullptr, *d_nfe = nullptr, *d_nje = nullptr, *d_nsteps = nullptr;
@@ -968,6 +972,7 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
     const size_t o_umap = take((umap.empty() ? 1 : n_in) * sizeof(int)), o_sel = take((sel.empty() ? 1 : n_in) * sizeof(int));
     const size_t o_counter0 = take(sizeof(unsigned long long));
     const size_t o_wfirst = take(nwarps * sizeof(int)), o_wcap = take(nwarps * sizeof(int));
+    const size_t o_nested = take(blocks * sizeof(int));
     const size_t in_bytes = (off + 255) & ~(size_t)255;
     off = in_bytes;
     const size_t o_z0 = take(n * sizeof(double)), o_nje = take(n * sizeof(unsigned)), o_nsteps = take(n * sizeof(unsigned));
@@ -996,6 +1001,7 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
     p->d_ov = (double*)(D + o_ov); p->d_Qout = (double*)(D + o_Qout); p->d_ia_out = (int*)(D + o_iaout);
     p->d_umap = (int*)(D + o_umap); p->d_sel = (int*)(D + o_sel);
     p->d_warp_first = (int*)(D + o_wfirst); p->d_warp_cap = (int*)(D + o_wcap);
+    p->d_block_nested = (int*)(D + o_nested);
     p->d_z0 = (double*)(D + o_z0); p->d_nje = (unsigned*)(D + o_nje); p->d_nsteps = (unsigned*)(D + o_nsteps);
     p->d_counter0 = (unsigned long long*)(D + o_counter0);
     p->d_counter = (unsigned long long*)(D + o_counter); p->d_block_smid = (int*)(D + o_smid);
@@ -1079,7 +1085,10 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         std::vector<int> border(blocks);
         for (int b = 0; b < (int)blocks; b++) border[b] = b;
         std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return smid[x] < smid[y]; });
-        const double GAIN = SONIC_SCHED_GAIN, KDEC = SONIC_SCHED_KDEC, T32 = 1.0 + GAIN;   // t(k) / t1, t(32) / t1
+        double GAIN = SONIC_SCHED_GAIN, KDEC = SONIC_SCHED_KDEC;
+        if (const char* e = getenv("SONIC_SCHED_GAIN")) GAIN = atof(e);      // (tuning runs)
+        if (const char* e = getenv("SONIC_SCHED_KDEC")) KDEC = atof(e);
+        const double T32 = 1.0 + GAIN;                                       // t(32) / t1
         std::vector<double> chain(n), tail(n + 1, 0.0);               // predicted ticks, suffix sums
         for (long long i = 0; i < n; i++) chain[i] = exp(cost[order[i]]);
         for (long long i = n - 1; i >= 0; i--) tail[i] = tail[i + 1] + chain[i];
@@ -1123,9 +1132,13 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         }
         p->n_initial = (unsigned long long)(pos < n ? pos : n);
         p->probe_smid = smid;
-        if (getenv("SONIC_DEBUG"))
-            fprintf(stderr, "[sonic] schedule: longest chain %.3g ticks, deadline %.2f x, predicted makespan %.2f x\n",
-                    chain[0], best_T / chain[0], best_span / chain[0]);
+        // The nested tick is used when no warp of the plan ever holds more than one point (small grids,
+        // single points: C1 -12 %).  On a grid that mixes sparse and full warps it is a loss even on SMs
+        // that host nothing but one-point warps (C2: 1.36 s instead of 1.26 s, profiles/README.md).
+        int* nested = (int*)(H + o_nested);
+        int mode = lpw == 1 ? 1 : 0;
+        if (const char* e = getenv("SONIC_NESTED")) mode = atoi(e);      // (experiments)
+        for (int b = 0; b < (int)blocks; b++) nested[b] = mode;
     }
     *(unsigned long long*)(H + o_counter0) = p->n_initial;
     // one upload of everything (or of the budgets alone when the probe already sent the rest)
@@ -1263,10 +1276,7 @@ int sonic_plan_launch(SonicPlan* p) {
     job.nsteps = p->d_nsteps; job.tpoint = p->d_tpoint; job.counter = p->d_counter; job.n = p->n;
     job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
     job.block_smid = p->d_block_smid; job.probe = 0;
-    // the nested tick only when no warp of the plan ever holds more than one point (small grids, single
-    // points): on an SM whose warps run both drivers the two instruction streams evict each other
-    job.lone_maxk = (SONIC_LONE_MAXK > 0 && p->lanes_per_warp == 1) ? SONIC_LONE_MAXK : 0;
-    if (const char* e = getenv("SONIC_LONE_MAXK")) job.lone_maxk = atoi(e);
+    job.block_nested = p->d_block_nested;
     cudaEvent_t* ev = p->ws->ev;
     p->result_on_host = false;
     CUDA_TRY(cudaMemcpyAsync(p->d_counter, p->d_counter0, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, p->stream));

@@ -41,7 +41,10 @@ def check_drive_phase(drive):
 
 def check_charges(Q, overtones=None):
     ''' Imposed charges (and the extrema of Fourier-series charge cycles) must lie in the physiological
-        range, with the reference's message (bls.py:674-677 `checkInputs`). '''
+        range, with the reference's message (bls.py:674-677 `checkInputs`).  The reference applies this
+        check to `simulate` calls only (model.py:169): `simCycles` / `computeEffVars` -- the lookup path
+        -- accept any charge (its own overtone grid reaches -107 - 2 x 100 nC/cm2), so the lookup entry
+        points run it on request only (`check_charge=True`). '''
     Qmin, Qmax = CHARGE_RANGE
     Q = np.atleast_1d(np.asarray(Q, dtype=float))
     lo, hi = Q, Q
@@ -71,7 +74,7 @@ class NeuronalBilayerSonophore(BilayerSonophore):
     def __repr__(self):
         return f'{self.__class__.__name__}({self.a * 1e9:.1f} nm, {self.pneuron})'
 
-    def effvars_batch(self, f, A, Q, fs, device=0, overtones=None, check_charge=True):
+    def effvars_batch(self, f, A, Q, fs, device=0, overtones=None, check_charge=False):
         ''' Effective variables for arrays of points (same radius).
             :param overtones: None, or charge overtones [n, novertones, 2] (amplitude C/m2, phase rad)
             :return: (tables[1+2*novertones+nrates, n, nfs], ncycles, status, tpoint, nrhs, stats) '''

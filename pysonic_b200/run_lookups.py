@@ -98,7 +98,7 @@ def overtone_refs(refs, novertones, test=False):
 
 def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
                        test=False, mpi=False, loglevel=logging.INFO, return_info=False,
-                       device=None, shard=True, check_charge=True):
+                       device=None, shard=True, check_charge=False):
     ''' Effective-variable lookup tables over (a, f, A, Q, fs).
 
         Drop-in for `computeAStimLookup` of scripts/run_lookups.py:22: same arguments (SI units:
@@ -110,8 +110,8 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
         Extra keyword arguments (not in the reference): `return_info` also returns the per-point
         cycle counts / status words / run statistics; `device` pins the run to one CUDA device;
         `shard=False` makes a rank under `torchrun` compute the whole grid on its own device;
-        `check_charge=False` skips the physiological-range check of the imposed charges (bls.py:674-677),
-        which the reference's own default overtone grid violates (-107 - 2 x 100 nC/cm2).
+        `check_charge=True` applies the physiological-range check of `checkInputs` (bls.py:674-677) to the
+        imposed charges; the reference runs that check for `simulate` only (model.py:169), not on this path.
 
         :return: Lookup (and, if return_info, a dict with ncycles/status/stats)
     '''
@@ -176,7 +176,7 @@ def computeAStimLookup(pneuron, aref, fref, Aref, fsref, Qref, novertones=0,
 
 
 def computeAStimLookups(pneurons, aref, fref, Aref, fsref, Qrefs, test=False, mpi=False,
-                        loglevel=logging.INFO, return_info=False, device=None, check_charge=True):
+                        loglevel=logging.INFO, return_info=False, device=None, check_charge=False):
     ''' Lookups of SEVERAL neurons over the same (a, f, A, fs) vectors in one batch: what the
         `for name in args['neuron']` loop of scripts/run_lookups.py:193-238 computes with one
         computeAStimLookup call per neuron.  All grids go through a single integrator launch
@@ -223,7 +223,7 @@ def _lib_max_overtones():
     return 4     # SONIC_MAX_OVERTONES of the native library
 
 
-def _overtones_lookup(pneuron, refs, novertones, test, loglevel, return_info, device, check_charge=True):
+def _overtones_lookup(pneuron, refs, novertones, test, loglevel, return_info, device, check_charge=False):
     ''' Lookup with charge overtones (run_lookups.py:105-128): every (a, f, A, Q) point is
         combined with every (AQ1, phiQ1, ..., AQn, phiQn) combination; the overtone dimensions come
         after Q and before fs, and every overtone adds the tables A_Vk, phi_Vk after V. '''

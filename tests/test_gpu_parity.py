@@ -373,13 +373,13 @@ def test_edge_cases(gpu):
     assert lkp['V'].shape == (1, 2, 2, 2, 1)
     np.testing.assert_array_equal(lkp.refs['f'], [500e3, 2e6])
     # a charge with no quasi-static equilibrium is reported, not silently integrated
-    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, 10.0, 1.0, check_charge=False)
+    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, 10.0, 1.0)
     with pytest.raises(ValueError, match='Invalid applied charge'):
-        nbls.effvars_batch(500e3, 1e5, 10.0, 1.0)           # bls.py:674-677
+        nbls.effvars_batch(500e3, 1e5, 10.0, 1.0, check_charge=True)           # bls.py:674-677, on request
     assert (status[0] & 16) and ncyc[0] == 0 and np.isnan(out).all()
     # an absurd charge that the integrator cannot follow is flagged (step failure / excess work),
     # its outputs are NaN, and the other points of the batch are unaffected
-    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, np.array([1.0, -71.9e-5]), 1.0, check_charge=False)
+    out, ncyc, status, _, _, _ = nbls.effvars_batch(500e3, 1e5, np.array([1.0, -71.9e-5]), 1.0)
     assert (status[0] & (4 | 8 | 16)) and np.isnan(out[:, 0]).all()
     assert status[1] == 0 and out[0, 1, 0] == pytest.approx(-136.78744984747215, rel=RTOL)
     # empty list and bad arguments are errors of the C ABI, not crashes

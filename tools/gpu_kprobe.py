@@ -41,4 +41,18 @@ for wl in ('c1', 'c2'):
     res[f'{wl}_ms'] = ms
     res[f'{wl}_hash'] = hashlib.sha256(out.tobytes() + ncyc.tobytes() + nrhs.tobytes()).hexdigest()[:12]
     plan.destroy()
+# one rank's share of the C2 table under 2 / 8-way strong scaling (trajectory groups dealt round-robin)
+from pysonic_b200.parallel import predicted_log_cost, shard_indices, trajectory_groups
+w = bench.workload('c2')
+bls = [ps.NeuronalBilayerSonophore(float(a), pn).abi_params() for a in w['a']]
+ia, f, A, Q = bench.flatten(w)
+cost = predicted_log_cost(w['a'][ia], f, A, Q); grp = trajectory_groups(ia, f, A, Q)
+for world in (2, 8):
+    idx = shard_indices(cost, 0, world, grp)
+    plan = _lib.Plan(0, bls, pn.neuron_id, 8, ia[idx], f[idx], A[idx], Q[idx], w['fs'])
+    ms = []
+    for _ in range(2):
+        plan.launch(); plan.sync(); ms.append(plan.stats()['ms_integrate'])
+    res[f'c2_shard_1_of_{world}_ms'] = ms
+    plan.destroy()
 print(json.dumps(res), flush=True)
