@@ -42,6 +42,10 @@
 #ifndef SONIC_LONE_MAXK
 #define SONIC_LONE_MAXK 1
 #endif
+/* SMs that keep one warp per scheduler for the longest chains (the other block of the SM is parked) */
+#ifndef SONIC_SCHED_EXCL_SMS
+#define SONIC_SCHED_EXCL_SMS 8
+#endif
 #ifndef SONIC_SCHED_GAIN
 #define SONIC_SCHED_GAIN 1.8
 #endif
@@ -188,6 +192,15 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     int cap = job.warp_cap[gwarp];
     long long q_init = (lane < cap) ? (long long)job.warp_first[gwarp] + lane : -1;
     bool exhausted = false;
+    if (cap == 0) {
+        // Parked warp: it shares its SM with the very longest chains of the grid, which then have a
+        // scheduler (and the SM's instruction cache) almost to themselves.  It stays out of the way
+        // until the shared queue is drained, then leaves.
+        if (lane == 0)
+            while (*reinterpret_cast<volatile unsigned long long*>(job.counter) < (unsigned long long)job.n) __nanosleep(20000);
+        __syncwarp();
+        cap = 32;
+    }
 
     while (true) {
         if (pt < 0 && !exhausted && lane < cap) {
@@ -1120,9 +1133,27 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
             if (span < best_span) { best_span = span; best_T = T; }
             if (queue <= T) break;        // larger T only makes the deadline later
         }
+        // The first `excl` SMs of the walk keep one warp per scheduler for the longest chains and
+        // park the others (blocks alternate on an SM; the probe tells which blocks share it).
+        int excl = SONIC_SCHED_EXCL_SMS;
+        if (const char* e = getenv("SONIC_SCHED_EXCL_SMS")) excl = atoi(e);
+        if (lpw <= 1 || blocks < 2 * (long long)dev.sm_count) excl = 0;     // only when the device is full
         long long pos = 0;
+        std::vector<int> excl_block(blocks, 0);
+        int sm_rank = -1, last_sm = -1, blk_on_sm = 0;
         for (int r = 0; r < nwarps; r++) {
-            const int gw = border[r / warps_per_block] * warps_per_block + r % warps_per_block;
+            const int b = border[r / warps_per_block];
+            const int gw = b * warps_per_block + r % warps_per_block;
+            if (r % warps_per_block == 0) {
+                if (smid[b] != last_sm) { last_sm = smid[b]; sm_rank++; blk_on_sm = 0; }
+                else blk_on_sm++;
+            }
+            if (sm_rank < excl) excl_block[b] = 1;
+            if (sm_rank < excl && blk_on_sm >= 1) {
+                wfirst[gw] = (int)n;
+                wcap[gw] = 0;                  // parked
+                continue;
+            }
             if (pos >= n) continue;
             int cap = cap_for(chain[pos], best_T);
             if (cap > (int)lpw) cap = (int)lpw;
@@ -1138,7 +1169,7 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         int* nested = (int*)(H + o_nested);
         int mode = lpw == 1 ? 1 : 0;
         if (const char* e = getenv("SONIC_NESTED")) mode = atoi(e);      // (experiments)
-        for (int b = 0; b < (int)blocks; b++) nested[b] = mode;
+        for (int b = 0; b < (int)blocks; b++) nested[b] = (mode == 2) ? excl_block[b] : mode;
     }
     *(unsigned long long*)(H + o_counter0) = p->n_initial;
     // one upload of everything (or of the budgets alone when the probe already sent the rest)
