@@ -219,7 +219,7 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None):
+def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None, device=0):
     ''' The literal north_star figures of this build against the reference-generated fixtures
         (tests/golden, made by tests/golden/make_goldens.py from the unmodified reference): BASELINE
         config 1 in full, and -- when the full RS 4-D table is at hand -- its 10 710 nodes of the dense
@@ -236,8 +236,9 @@ def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None):
 
     g = np.load(os.path.join(gold, 'c1_RS_32nm_500kHz.npz'))
     keys = [str(k) for k in g['keys']]
+    # (this rank alone, on its own device: no collective, the other ranks are not here)
     lkp, info = ps.computeAStimLookup(ps.getPointNeuron('RS'), g['a'], g['f'], g['A'], g['fs'], g['Q'],
-                                      return_info=True, loglevel=10)
+                                      return_info=True, loglevel=10, device=device, shard=False)
     out['c1_full_1000_points'] = parity_stats(lkp.tables, info['ncycles'], g, variants('c1_RS_32nm_500kHz'), keys)
     big = os.path.join(gold, 'c2_RS_big.npz')
     if lkp_c2 is not None and os.path.isfile(big) and len(variants('c2_RS_big')) == 2:
@@ -278,7 +279,8 @@ def gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -395,7 +397,7 @@ def gpu_arm(args):
     # ---- extras (rank 0, outside every timed region) ----
     parity = multi = None
     if rank == 0 and not args.no_extras:
-        parity = live_parity(ps, lkp if args.workload == 'c2' else None, info, w)
+        parity = live_parity(ps, lkp if args.workload == 'c2' else None, info, w, device=local_rank)
     if world == 1 and not args.no_extras and args.workload == 'c2':
         names = ['RS', 'FS', 'LTS', 'IB']
         pns = [ps.getPointNeuron(x) for x in names]

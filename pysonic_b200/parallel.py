@@ -115,9 +115,13 @@ def trajectory_groups(ia, f, A, Q):
         sonic_plan_create_ex does. '''
     q = np.abs(np.ascontiguousarray(Q, dtype=np.float64))
     qb = (q.view(np.uint64) + np.uint64(0x8000)) & ~np.uint64(0xFFFF)
-    key = np.stack([np.asarray(ia).astype(np.uint64), np.ascontiguousarray(f, dtype=np.float64).view(np.uint64),
-                    np.ascontiguousarray(A, dtype=np.float64).view(np.uint64), qb], axis=1)
-    _, inv = np.unique(key, axis=0, return_inverse=True)
+    # one integer id per column (few distinct values each), combined into a single key
+    key = np.zeros(q.size, dtype=np.int64)
+    for col in (np.asarray(ia).astype(np.int64), np.ascontiguousarray(f, dtype=np.float64).view(np.int64),
+                np.ascontiguousarray(A, dtype=np.float64).view(np.int64), qb.view(np.int64)):
+        vals, inv = np.unique(col, return_inverse=True)
+        key = key * vals.size + inv.ravel()
+    _, inv = np.unique(key, return_inverse=True)
     return inv.ravel()
 
 
@@ -140,12 +144,12 @@ def shard_indices(cost, rank, world_size, groups=None):
 
 
 def gather_slabs(n, idx, arrays, rank, world_size):
-    ''' Gather per-point outputs from all ranks into full arrays (on every rank).
+    ''' Gather per-point outputs from all ranks into full arrays (on every rank): ONE all_gather of a
+        byte matrix whose rows are [global index | the point's slice of every array].
 
         :param n: total number of points
         :param idx: indices owned by this rank
-        :param arrays: list of arrays whose LAST-BUT-`k` axis layout is (..., len(idx), ...):
-            each array is given as (array, axis) with `axis` the point axis
+        :param arrays: list of (array, axis) with `axis` the point axis of the array
         :return: list of full arrays with `n` along the point axis
     '''
     import torch
@@ -153,32 +157,40 @@ def gather_slabs(n, idx, arrays, rank, world_size):
     backend = dist.get_backend()
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))) if backend == 'nccl' \
         else torch.device('cpu')
-    # sizes differ by at most one between ranks: pad to the max
     m = int(len(idx))
+    # rows: raw bytes (NCCL has no unsigned 32-bit type for the status words and RHS counts)
+    cols = [np.ascontiguousarray(np.asarray(idx, dtype=np.int64)).view(np.uint8).reshape(m, 8)]
+    moved = []
+    for arr, axis in arrays:
+        a = np.ascontiguousarray(np.moveaxis(np.asarray(arr), axis, 0))
+        moved.append(a)
+        cols.append(a.view(np.uint8).reshape(m, -1) if m else np.zeros((0, a[0:1].nbytes if a.size else a.dtype.itemsize * int(np.prod(a.shape[1:]))), np.uint8))
+    rowbytes = sum(c.shape[1] for c in cols)
+    # shard sizes differ by a few points at most (whole trajectory groups are dealt): pad to the largest
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world_size)]
     dist.all_gather(sizes, torch.tensor([m], dtype=torch.int64, device=dev))
-    sizes = [int(s.item()) for s in sizes]
+    sizes = [int(x.item()) for x in sizes]
     mmax = max(sizes)
-    idx_pad = np.full(mmax, -1, dtype=np.int64)
-    idx_pad[:m] = idx
-    all_idx = [torch.zeros(mmax, dtype=torch.int64, device=dev) for _ in range(world_size)]
-    dist.all_gather(all_idx, torch.from_numpy(idx_pad).to(dev))
-    all_idx = [t.cpu().numpy() for t in all_idx]
+    mat = np.zeros((mmax, rowbytes), dtype=np.uint8)
+    if m:
+        mat[:m] = np.concatenate(cols, axis=1)
+    t = torch.from_numpy(mat.reshape(-1)).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world_size)]
+    dist.all_gather(parts, t)
+    parts = [x.cpu().numpy().reshape(mmax, rowbytes) for x in parts]
     out = []
-    for arr, axis in arrays:
-        arr = np.moveaxis(np.asarray(arr), axis, 0)
-        pad = np.zeros((mmax,) + arr.shape[1:], dtype=arr.dtype)
-        pad[:m] = arr
-        # ship raw bytes: NCCL has no unsigned 32-bit type (status words, RHS counts)
-        t = torch.from_numpy(np.ascontiguousarray(pad).view(np.uint8).reshape(-1)).to(dev)
-        parts = [torch.zeros_like(t) for _ in range(world_size)]
-        dist.all_gather(parts, t)
-        full = np.zeros((n,) + arr.shape[1:], dtype=arr.dtype)
+    off = 8
+    for (arr, axis), a in zip(arrays, moved):
+        width = int(np.prod(a.shape[1:])) * a.dtype.itemsize
+        full = np.zeros((n,) + a.shape[1:], dtype=a.dtype)
         for r in range(world_size):
             k = sizes[r]
-            part = parts[r].cpu().numpy().view(arr.dtype).reshape(pad.shape)
-            full[all_idx[r][:k]] = part[:k]
+            if k == 0:
+                continue
+            gidx = np.ascontiguousarray(parts[r][:k, :8]).view(np.int64).ravel()
+            full[gidx] = np.ascontiguousarray(parts[r][:k, off:off + width]).view(a.dtype).reshape((k,) + a.shape[1:])
         out.append(np.moveaxis(full, 0, axis))
+        off += width
     return out
 
 

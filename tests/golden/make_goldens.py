@@ -11,6 +11,9 @@
         python tests/golden/make_goldens.py c2sub       # stratified subsample of RS-4D (C2)
         python tests/golden/make_goldens.py noise       # reference re-run with +-2 ulp amplitude
         python tests/golden/make_goldens.py noise4      # small grids re-run with +-4 ulp amplitude
+        python tests/golden/make_goldens.py c2big       # dense RS 4-D fixture (+-2 ulp amplitude re-runs)
+        python tests/golden/make_goldens.py c2big_q     # ... re-run with the charge changed by +-2 ulp (_ulp_up2/_dn2)
+        python tests/golden/make_goldens.py neurons_big # >= 1000-point fixtures for the C3-C5 neurons
         python tests/golden/make_goldens.py all
 
     Every record is produced by `NeuronalBilayerSonophore.computeEffVars`
@@ -235,11 +238,14 @@ def gen_rates():
     print('rates_sweep.json:', len(names), 'neurons x', Vm.size, 'potentials')
 
 
-def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref, amp_scale=1.0):
+def _grid_to_npz(fname, name, aref, fref, Aref, Qref, fsref, amp_scale=1.0, q_scale=1.0):
     # amp_scale != 1 (a 1-2 ulp relative change of the drive amplitude) is used to measure the
     # reference's own reproducibility floor: how far its outputs move under a rounding-level
     # perturbation of its inputs.
-    jobs = [(name, a, f, A * amp_scale, Q, list(fsref))
+    # (q_scale != 1: the same for the imposed charge -- a rounding-level change of the drive amplitude is
+    #  invisible below ~1 kPa, where the drive is a 1e-3 ... 1e-2 fraction of the static pressures, so the
+    #  low-amplitude rows need a perturbation that reaches the dynamics)
+    jobs = [(name, a, f, A * amp_scale, Q * q_scale, list(fsref))
             for a in aref for f in fref for A in Aref for Q in Qref]
     t0 = time.perf_counter()
     recs = pmap(jobs)
@@ -292,12 +298,12 @@ def gen_c2sub(amp_scale=1.0, tag=''):
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], A, Q, [1.0], amp_scale)
 
 
-def gen_c2big(amp_scale=1.0, tag=''):
+def gen_c2big(amp_scale=1.0, tag='', q_scale=1.0):
     ''' Dense subsample of the RS 4-D default grid: every radius, frequency and amplitude (the
         16 nm / 20 kHz heavy rows included), every 16th charge -> 3 x 7 x 51 x 10 = 10 710 points. '''
     _grid_to_npz(f'c2_RS_big{tag}.npz', 'RS', [16e-9, 32e-9, 64e-9],
                  [20e3, 100e3, 500e3, 1e6, 2e6, 3e6, 4e6], c2_amps(), default_charges('RS')[::16], [1.0],
-                 amp_scale)
+                 amp_scale, q_scale)
 
 
 def gen_neurons_big(amp_scale=1.0, tag=''):
@@ -399,10 +405,12 @@ if __name__ == '__main__':
                                  gen_cortical(1.0 - 4.440892098500626e-16, '_ulp_dn')), 'overtones': gen_overtones, 'noise': gen_noise,
             'c2big': lambda: (gen_c2big(), gen_c2big(1.0 + 4.440892098500626e-16, '_ulp_up'),
                               gen_c2big(1.0 - 4.440892098500626e-16, '_ulp_dn')),
+            'c2big_q': lambda: (gen_c2big(1.0, '_ulp_up2', 1.0 + 4.440892098500626e-16),
+                                gen_c2big(1.0, '_ulp_dn2', 1.0 - 4.440892098500626e-16)),
             'neurons_big': lambda: (gen_neurons_big(), gen_neurons_big(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                     gen_neurons_big(1.0 - 4.440892098500626e-16, '_ulp_dn')),
             'noise_neurons': lambda: (gen_neurons(1.0 + 4.440892098500626e-16, '_ulp_up'),
                                       gen_neurons(1.0 - 4.440892098500626e-16, '_ulp_dn'))}
     for k, fn in todo.items():
-        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4', 'c2big', 'neurons_big', 'points2')):
+        if what == k or (what == 'all' and k not in ('noise_neurons', 'overtones', 'cm', 'cortical', 'noise4', 'c2big', 'c2big_q', 'neurons_big', 'points2')):
             fn()
