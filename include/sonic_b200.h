@@ -34,6 +34,9 @@
  *                         plan: what scripts/run_Cm_lookups.py:19-64 tabulates.
  *   sonic_pmavg        <- BilayerSonophore.PMavg / v_PMavg (bls.py:390-408): the quadrature behind the
  *                         Lennard-Jones fit of computePMparams (bls.py:410-470), batched over Z.
+ *   sonic_simulate     <- NeuronalBilayerSonophore.__simSonic (nbls.py:389-437): effDerivatives (:280-315) with
+ *                         Lookup.project / interpolate1D (lookups.py:234-333) integrated over the sample
+ *                         times of EventDrivenSolver (solvers.py:445-478), batched over simulations.
  *   sonic_mean_rates   <- PointNeuron.getEffRates(Vm) (pneuron.py:268-271).
  *   sonic_eval_rates   <- the neuron's alphax/betax/xinf/taux methods evaluated elementwise
  *                         (PySONIC/neurons/*.py), for testing the generated device functions.
@@ -201,6 +204,23 @@ int sonic_plan_destroy(SonicPlan* plan);
  * QAGS, epsabs = epsrel = 1.49e-8, 50 sub-intervals at most) of the leaflet force 2 pi r PMlocal(r) over
  * [0, a], divided by the stretched surface.  out_last (optional): sub-intervals used per deflection. */
 int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, double* out_pm, int32_t* out_last);
+
+/* SONIC simulations on the tables, batched: simulation i integrates  dQm/dt = -iNet(V, x) 1e-3,
+ * dx_k/dt = alpha_k (1 - x_k) - beta_k x_k  with V, alpha_k, beta_k interpolated linearly in Qm from
+ * tab_on[i] while the stimulus is on and from tab_off otherwise ([1 + 2 NS][nQ] each: V, then the
+ * (alpha, beta) pair of every gating state in the neuron's rate order; NS = sonic_sim_nstates).
+ *   t[nt]        : sample times (non-decreasing; equal consecutive times repeat the state, as the
+ *                  reference's solver does at every stimulus transition)
+ *   stim_on[nt]  : stimulus state of the interval that ends at sample i
+ *   y0[1 + NS]   : initial charge (C/m2) and states
+ *   nsub         : integrator sub-steps between consecutive samples
+ *   out          : [nsim][nt][1 + NS];  status[nsim]: 1 = the charge left the tabulated range (rows are
+ *                  NaN from there on; the reference raises ValueError in that case) */
+int sonic_simulate(int device, int neuron_id, int nsim, int nQ, const double* Qref, const double* tab_on,
+                   const double* tab_off, int nt, const double* t, const uint8_t* stim_on, const double* y0, int nsub,
+                   double* out, int32_t* status);
+/* Number of gating states of the neuron's SONIC simulation (0: not supported). */
+int sonic_sim_nstates(int neuron_id);
 
 /* Releases the idle workspaces (one device allocation + one pinned host buffer + stream per plan,
  * kept per device between calls; up to 8 kB of device memory per point): call it when no further

@@ -12,6 +12,7 @@ from .bls import BilayerSonophore  # noqa: F401
 from .nbls import NeuronalBilayerSonophore  # noqa: F401
 from .batches import Batch  # noqa: F401
 from .lookups import Lookup  # noqa: F401
+from .protocols import PulsedProtocol  # noqa: F401
 from .run_lookups import computeAStimLookup, computeAStimLookups  # noqa: F401
 from .run_cm_lookups import computeCmLookup  # noqa: F401
 

@@ -75,6 +75,9 @@ EXPORTS = {
     'sonic_plan_stats': (C.c_int, [C.c_void_p, _sp]),
     'sonic_plan_destroy': (C.c_int, [C.c_void_p]),
     'sonic_pmavg': (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int64, _dp, _dp, _ip]),
+    'sonic_simulate': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp,
+                                 C.POINTER(C.c_uint8), _dp, C.c_int, _dp, _ip]),
+    'sonic_sim_nstates': (C.c_int, [C.c_int]),
     'sonic_trim': (C.c_int, []),
     'sonic_fp64_peak': (C.c_int, [C.c_int, _dp]),
 }
@@ -329,3 +332,19 @@ def pmavg(a, Delta, Z, device=0, with_last=False):
     last = np.empty(Z.size, dtype=np.int32)
     check(lib.sonic_pmavg(device, float(a), float(Delta), Z.size, _d(Z), _d(out), last.ctypes.data_as(_ip)))
     return (out, last) if with_last else out
+
+
+def simulate(neuron_id, Qref, tab_on, tab_off, t, stim_on, y0, nsub=64, device=0):
+    ''' Batched SONIC simulations on 1-D lookups (sonic_simulate).
+        :param tab_on: [nsim, 1 + 2 NS, nQ];  tab_off: [1 + 2 NS, nQ]
+        :return: (out[nsim, nt, 1 + NS], status[nsim]) '''
+    lib = load()
+    Qref, tab_on, tab_off, t, y0 = as_f64(Qref), as_f64(tab_on), as_f64(tab_off), as_f64(t), as_f64(y0)
+    stim_on = np.ascontiguousarray(stim_on, dtype=np.uint8)
+    nsim, nv, nQ = tab_on.shape
+    out = np.empty((nsim, t.size, y0.size))
+    status = np.empty(nsim, dtype=np.int32)
+    check(lib.sonic_simulate(device, neuron_id, nsim, nQ, _d(Qref), _d(tab_on), _d(tab_off), t.size, _d(t),
+                             stim_on.ctypes.data_as(C.POINTER(C.c_uint8)), _d(y0), int(nsub), _d(out),
+                             status.ctypes.data_as(_ip)))
+    return out, status

@@ -16,7 +16,7 @@
 
 import os
 
-from .neurons import NEURON_SPECS, NEURON_ORDER, Gate, Rate, spec_rate_names, MAX_RATES
+from .neurons import NEURON_SPECS, NEURON_ORDER, NEURON_SIM, Gate, Rate, spec_rate_names, MAX_RATES
 
 HEADER = '''// GENERATED FILE -- do not edit.  Produced by pysonic_b200/codegen.py from pysonic_b200/neurons.py.
 // Voltage-dependent rate constants (s^-1) of every supported point neuron, as device functions.
@@ -29,6 +29,13 @@ HEADER = '''// GENERATED FILE -- do not edit.  Produced by pysonic_b200/codegen.
 static __device__ __forceinline__ double vtrap(double x, double y) {{ return x / (exp(x / y) - 1); }}
 
 template <int ID> struct SonicRates;
+
+// Net membrane current (mA/m2) of the neurons whose SONIC simulation is supported (NS = number of gating
+// states, state k <-> rates 2k and 2k + 1 of SonicRates<ID>); NS = 0: not supported.
+template <int ID> struct SonicSim {{
+    static constexpr int NS = 0;
+    static __device__ __forceinline__ double inet(double, const double*) {{ return 0.0; }}
+}};
 '''
 
 
@@ -62,6 +69,19 @@ def gen_neuron(nid, name):
         lines.append(f'        (void){k};')
     lines.append('        (void)Vm; (void)r;')
     lines += ['    }', '};', '']
+    if name in NEURON_SIM:
+        sim = NEURON_SIM[name]
+        rates = spec_rate_names(name)
+        for k, st in enumerate(sim['states']):
+            assert rates[2 * k] == f'alpha{st}' and rates[2 * k + 1] == f'beta{st}', (name, st)
+        assert len(rates) == 2 * len(sim['states']), name
+        lines += [f'template <> struct SonicSim<{nid}> {{', f"    static constexpr int NS = {len(sim['states'])};",
+                  '    static __device__ __forceinline__ double inet(const double Vm, const double* x) {']
+        for k, v in sim['consts'].items():
+            lines.append(f'        const double {k} = {_fmt(v)};')
+        for k, st in enumerate(sim['states']):
+            lines.append(f'        const double {st} = x[{k}];')
+        lines += [f"        return {sim['inet']};", '    }', '};', '']
     return '\n'.join(lines)
 
 

@@ -10,6 +10,13 @@ static __device__ __forceinline__ double vtrap(double x, double y) { return x / 
 
 template <int ID> struct SonicRates;
 
+// Net membrane current (mA/m2) of the neurons whose SONIC simulation is supported (NS = number of gating
+// states, state k <-> rates 2k and 2k + 1 of SonicRates<ID>); NS = 0: not supported.
+template <int ID> struct SonicSim {
+    static constexpr int NS = 0;
+    static __device__ __forceinline__ double inet(double, const double*) { return 0.0; }
+};
+
 // ---- RS ----
 template <> struct SonicRates<0> {
     static constexpr int N = 8;
@@ -32,6 +39,24 @@ template <> struct SonicRates<0> {
     }
 };
 
+template <> struct SonicSim<0> {
+    static constexpr int NS = 4;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 560.0;
+        const double ENa = 50.0;
+        const double gKdbar = 60.0;
+        const double EK = -90.0;
+        const double gMbar = 0.75;
+        const double gLeak = 0.205;
+        const double ELeak = -70.3;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double p = x[3];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak);
+    }
+};
+
 // ---- FS ----
 template <> struct SonicRates<1> {
     static constexpr int N = 8;
@@ -51,6 +76,24 @@ template <> struct SonicRates<1> {
         (void)VT;
         (void)TauMax;
         (void)Vm; (void)r;
+    }
+};
+
+template <> struct SonicSim<1> {
+    static constexpr int NS = 4;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 580.0;
+        const double ENa = 50.0;
+        const double gKdbar = 39.0;
+        const double EK = -90.0;
+        const double gMbar = 0.787;
+        const double gLeak = 0.38;
+        const double ELeak = -70.4;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double p = x[3];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak);
     }
 };
 
@@ -87,6 +130,28 @@ template <> struct SonicRates<2> {
     }
 };
 
+template <> struct SonicSim<2> {
+    static constexpr int NS = 6;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 500.0;
+        const double ENa = 50.0;
+        const double gKdbar = 40.0;
+        const double EK = -90.0;
+        const double gMbar = 0.28;
+        const double gLeak = 0.19;
+        const double ELeak = -50.0;
+        const double gCaTbar = 4.0;
+        const double ECa = 120.0;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double p = x[3];
+        const double s = x[4];
+        const double u = x[5];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak) + gCaTbar * s * s * u * (Vm - ECa);
+    }
+};
+
 // ---- IB ----
 template <> struct SonicRates<3> {
     static constexpr int N = 12;
@@ -113,6 +178,28 @@ template <> struct SonicRates<3> {
     }
 };
 
+template <> struct SonicSim<3> {
+    static constexpr int NS = 6;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 500.0;
+        const double ENa = 50.0;
+        const double gKdbar = 50.0;
+        const double EK = -90.0;
+        const double gMbar = 0.3;
+        const double gLeak = 0.1;
+        const double ELeak = -70.0;
+        const double gCaLbar = 1.0;
+        const double ECa = 120.0;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double p = x[3];
+        const double q = x[4];
+        const double r = x[5];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak) + gCaLbar * q * q * r * (Vm - ECa);
+    }
+};
+
 // ---- RE ----
 template <> struct SonicRates<4> {
     static constexpr int N = 10;
@@ -134,6 +221,26 @@ template <> struct SonicRates<4> {
         r[9] = (1 - inf_u) / tau_u;
         (void)VT;
         (void)Vm; (void)r;
+    }
+};
+
+template <> struct SonicSim<4> {
+    static constexpr int NS = 5;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 2000.0;
+        const double ENa = 50.0;
+        const double gKdbar = 200.0;
+        const double EK = -90.0;
+        const double gCaTbar = 30.0;
+        const double ECa = 120.0;
+        const double gLeak = 0.5;
+        const double ELeak = -90.0;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double s = x[3];
+        const double u = x[4];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gCaTbar * s * s * u * (Vm - ECa) + gLeak * (Vm - ELeak);
     }
 };
 
@@ -246,6 +353,19 @@ template <> struct SonicRates<8> {
     }
 };
 
+template <> struct SonicSim<8> {
+    static constexpr int NS = 2;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 14450.0;
+        const double ENa = 35.64;
+        const double gLeak = 1280.0;
+        const double ELeak = -80.01;
+        const double m = x[0];
+        const double h = x[1];
+        return gNabar * m * m * h * (Vm - ENa) + gLeak * (Vm - ELeak);
+    }
+};
+
 // ---- MRGnode ----
 template <> struct SonicRates<9> {
     static constexpr int N = 8;
@@ -267,6 +387,24 @@ template <> struct SonicRates<9> {
         (void)q10_h;
         (void)q10_s;
         (void)Vm; (void)r;
+    }
+};
+
+template <> struct SonicSim<9> {
+    static constexpr int NS = 4;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNafbar = 30000.0;
+        const double gNapbar = 100.0;
+        const double ENa = 50.0;
+        const double gKsbar = 800.0;
+        const double EK = -90.0;
+        const double gLeak = 70.0;
+        const double ELeak = -90.0;
+        const double m = x[0];
+        const double h = x[1];
+        const double p = x[2];
+        const double s = x[3];
+        return gNafbar * m * m * m * h * (Vm - ENa) + gNapbar * p * p * p * (Vm - ENa) + gKsbar * s * (Vm - EK) + gLeak * (Vm - ELeak);
     }
 };
 
@@ -298,6 +436,23 @@ template <> struct SonicRates<10> {
     }
 };
 
+template <> struct SonicSim<10> {
+    static constexpr int NS = 4;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 400.0;
+        const double ENa = 55.0;
+        const double gKdbar = 400.0;
+        const double EK = -90.0;
+        const double gLeak = 1.0;
+        const double ELeak = -60.069175300110516;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        const double l = x[3];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * l * (Vm - EK) + gLeak * (Vm - ELeak);
+    }
+};
+
 // ---- HHseg ----
 template <> struct SonicRates<11> {
     static constexpr int N = 6;
@@ -311,6 +466,22 @@ template <> struct SonicRates<11> {
         r[5] = q10 * 0.125 * exp(-(Vm + 65) / 80) * 1e3;
         (void)q10;
         (void)Vm; (void)r;
+    }
+};
+
+template <> struct SonicSim<11> {
+    static constexpr int NS = 3;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 1200.0;
+        const double ENa = 50.0;
+        const double gKdbar = 360.0;
+        const double EK = -77.0;
+        const double gLeak = 3.0;
+        const double ELeak = -54.3;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gLeak * (Vm - ELeak);
     }
 };
 
@@ -368,6 +539,22 @@ template <> struct SonicRates<14> {
         r[5] = 0.5 * exp(-((Vm - VT) - 10) / 40) * 1e3;
         (void)VT;
         (void)Vm; (void)r;
+    }
+};
+
+template <> struct SonicSim<14> {
+    static constexpr int NS = 3;
+    static __device__ __forceinline__ double inet(const double Vm, const double* x) {
+        const double gNabar = 560.0;
+        const double ENa = 50.0;
+        const double gKdbar = 60.0;
+        const double EK = -90.0;
+        const double gLeak = 0.205;
+        const double ELeak = -70.3;
+        const double m = x[0];
+        const double h = x[1];
+        const double n = x[2];
+        return gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK) + gLeak * (Vm - ELeak);
     }
 };
 

@@ -484,6 +484,109 @@ __global__ void __launch_bounds__(64) sonic_pmavg_kernel(double a, double Delta,
     if (last) last[i] = l;
 }
 
+// ---------------------------------------------------------------------------------------
+// SONIC simulation on the tables (nbls.py:280-315,389-437): one thread per simulation integrates the
+// effective system  dQm/dt = -iNet(V_eff(Qm), x) 1e-3,  dx_k/dt = alpha_k(Qm) (1 - x_k) - beta_k(Qm) x_k
+// whose coefficients are interpolated linearly in the charge from the 1-D lookups of the stimulus-on and
+// stimulus-off conditions (Lookup.project('A', .), interpolate1D: lookups.py:234-333), over the sample
+// times the reference's EventDrivenSolver produces (solvers.py:445-478).  The effective rates reach
+// 1e6 ... 1e16 s^-1 in parts of the tables, so the gates are advanced with the exact solution of their
+// linear equation over each sub-step (rates frozen at the mid-point charge) and the charge with the
+// mid-point rule: second order, unconditionally stable in the gates.
+// ---------------------------------------------------------------------------------------
+struct SonicSimArgs {
+    const double* Qref;        // [nQ] ascending
+    const double* tab_on;      // [nsim][1 + 2 NS][nQ]: V, alpha_k, beta_k at the drive amplitude of each simulation
+    const double* tab_off;     // [1 + 2 NS][nQ] at zero amplitude (shared)
+    const double* t;           // [nt] sample times
+    const unsigned char* on;   // [nt] stimulus state of the interval that ends at sample i
+    const double* y0;          // [1 + NS]
+    double* out;               // [nsim][nt][1 + NS]
+    int* status;               // [nsim]: 0 ok, 1 charge left the tabulated range (the reference raises there)
+    int nsim, nQ, nt, nsub;
+};
+
+template <int NS>
+static __device__ __forceinline__ bool sonic_sim_lookup(const double* __restrict__ tab, const double* __restrict__ Qref, int nQ,
+                                                        double Q, double* V, double* al, double* be) {
+    if (!(Q >= Qref[0] && Q <= Qref[nQ - 1])) return false;
+    int lo = 0, hi = nQ - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (Qref[mid] <= Q) lo = mid;
+        else hi = mid;
+    }
+    const double w = (Q - Qref[lo]) / (Qref[hi] - Qref[lo]);
+    *V = tab[lo] + w * (tab[hi] - tab[lo]);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+        const double* a = tab + (size_t)(1 + 2 * k) * nQ;
+        const double* b = a + nQ;
+        al[k] = a[lo] + w * (a[hi] - a[lo]);
+        be[k] = b[lo] + w * (b[hi] - b[lo]);
+    }
+    return true;
+}
+
+template <int NID>
+__global__ void __launch_bounds__(64) sonic_simulate_kernel(SonicSimArgs a) {
+    constexpr int NS = SonicSim<NID>::NS;
+    constexpr int NSA = NS > 0 ? NS : 1;
+    const int sim = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sim >= a.nsim) return;
+    const int nQ = a.nQ, NV = 1 + 2 * NS;
+    const double* on = a.tab_on + (size_t)sim * NV * nQ;
+    double Q = a.y0[0], x[NSA];
+#pragma unroll
+    for (int k = 0; k < NS; k++) x[k] = a.y0[1 + k];
+    double* out = a.out + (size_t)sim * a.nt * (1 + NS);
+    out[0] = Q;
+#pragma unroll
+    for (int k = 0; k < NS; k++) out[1 + k] = x[k];
+    int st = 0;
+    for (int i = 1; i < a.nt; i++) {
+        const double h = a.t[i] - a.t[i - 1];
+        if (h > 0.0 && st == 0) {
+            const double* tab = a.on[i] ? on : a.tab_off;
+            const double hs = h / a.nsub;
+            for (int s = 0; s < a.nsub; s++) {
+                double V, al[NSA], be[NSA];
+                if (!sonic_sim_lookup<NS>(tab, a.Qref, nQ, Q, &V, al, be)) { st = 1; break; }
+                const double Qh = Q - 0.5 * hs * (SonicSim<NID>::inet(V, x) * 1e-3);
+                if (!sonic_sim_lookup<NS>(tab, a.Qref, nQ, Qh, &V, al, be)) { st = 1; break; }
+                double xm[NSA];
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const double r = al[k] + be[k];
+                    if (r > 0.0) {
+                        const double xinf = al[k] / r;
+                        const double e = exp(-0.5 * hs * r);
+                        xm[k] = xinf + (x[k] - xinf) * e;
+                        x[k] = xinf + (xm[k] - xinf) * e;
+                    } else {
+                        xm[k] = x[k];
+                    }
+                }
+                Q -= hs * (SonicSim<NID>::inet(V, xm) * 1e-3);
+            }
+        }
+        double* o = out + (size_t)i * (1 + NS);
+        o[0] = st ? nan("") : Q;
+#pragma unroll
+        for (int k = 0; k < NS; k++) o[1 + k] = st ? nan("") : x[k];
+    }
+    a.status[sim] = st;
+}
+
+template <int NID>
+static cudaError_t launch_simulate(const SonicSimArgs& a) {
+    sonic_simulate_kernel<NID><<<(a.nsim + 63) / 64, 64>>>(a);
+    return cudaGetLastError();
+}
+
+template <int NID>
+static int sim_nstates() { return SonicSim<NID>::NS; }
+
 // FP64 FMA peak: 8 independent register chains per thread.
 __global__ void __launch_bounds__(256) sonic_dfma_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
@@ -1697,6 +1800,67 @@ int sonic_pmavg(int device, double a, double Delta, int64_t n, const double* Z, 
     if (e == cudaSuccess && out_last) e = cudaMemcpy(out_last, d_last, n * sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(d_Z);
     if (e != cudaSuccess) return set_err(SONIC_E_CUDA, "intermolecular pressure quadrature failed: %s", cudaGetErrorString(e));
+    return SONIC_OK;
+}
+
+int sonic_sim_nstates(int neuron_id) {
+    if (neuron_id < 0 || neuron_id >= SONIC_N_NEURONS) return set_err(SONIC_E_NEURON, "unknown neuron id %d", neuron_id);
+    int ns = 0;
+#define CALL(ID) ns = sim_nstates<ID>()
+    SONIC_DISPATCH_NEURON(neuron_id, CALL)
+#undef CALL
+    return ns;
+}
+
+int sonic_simulate(int device, int neuron_id, int nsim, int nQ, const double* Qref, const double* tab_on,
+                   const double* tab_off, int nt, const double* t, const uint8_t* stim_on, const double* y0, int nsub,
+                   double* out, int32_t* status) {
+    int rc = check_device(device);
+    if (rc) return rc;
+    const int ns = sonic_sim_nstates(neuron_id);
+    if (ns < 0) return ns;
+    if (ns == 0) return set_err(SONIC_E_NEURON, "the SONIC simulation of neuron %d is not supported (states that are not gates)", neuron_id);
+    if (nsim <= 0 || nQ < 2 || nt < 2 || nsub < 1 || !Qref || !tab_on || !tab_off || !t || !stim_on || !y0 || !out || !status)
+        return set_err(SONIC_E_ARG, "invalid argument (null pointer or empty dimension)");
+    for (int i = 1; i < nQ; i++)
+        if (!(Qref[i] > Qref[i - 1])) return set_err(SONIC_E_ARG, "charge vector must be strictly ascending");
+    for (int i = 1; i < nt; i++)
+        if (!(t[i] >= t[i - 1])) return set_err(SONIC_E_ARG, "sample times must not decrease");
+    CUDA_TRY(cudaSetDevice(device));
+    const int nv = 1 + 2 * ns;
+    const size_t b_Q = (size_t)nQ * 8, b_on = (size_t)nsim * nv * nQ * 8, b_off = (size_t)nv * nQ * 8, b_t = (size_t)nt * 8;
+    const size_t b_y0 = (size_t)(1 + ns) * 8, b_out = (size_t)nsim * nt * (1 + ns) * 8, b_st = (size_t)nsim * 4;
+    const size_t b_s = ((size_t)nt + 7) & ~(size_t)7;
+    char* d = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d), b_Q + b_on + b_off + b_t + b_y0 + b_out + b_st + b_s);
+    SonicSimArgs a;
+    if (e == cudaSuccess) {
+        char* q = d;
+        a.Qref = (double*)q; q += b_Q;
+        a.tab_on = (double*)q; q += b_on;
+        a.tab_off = (double*)q; q += b_off;
+        a.t = (double*)q; q += b_t;
+        a.y0 = (double*)q; q += b_y0;
+        a.out = (double*)q; q += b_out;
+        a.status = (int*)q; q += b_st;
+        a.on = (unsigned char*)q;
+        a.nsim = nsim; a.nQ = nQ; a.nt = nt; a.nsub = nsub;
+        e = cudaMemcpy((void*)a.Qref, Qref, b_Q, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy((void*)a.tab_on, tab_on, b_on, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)a.tab_off, tab_off, b_off, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)a.t, t, b_t, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)a.y0, y0, b_y0, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)a.on, stim_on, nt, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+#define CALL(ID) e = launch_simulate<ID>(a)
+        SONIC_DISPATCH_NEURON(neuron_id, CALL)
+#undef CALL
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, a.out, b_out, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(status, a.status, b_st, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(SONIC_E_CUDA, "SONIC simulation failed: %s", cudaGetErrorString(e));
     return SONIC_OK;
 }
 

@@ -212,6 +212,62 @@ NEURON_SPECS = {
     'pas': dict(Cm0=1e-2, Vm0=-70., consts={}, kin=[]),
 }
 
+
+# ---------------------------------------------------------------------------------------------
+# Membrane currents for the SONIC simulation that consumes the tables (nbls.py:280-315,389-437):
+# dQm/dt = -iNet(V_eff, x) * 1e-3, dx/dt = alpha_eff (1 - x) - beta_eff x with every effective quantity
+# interpolated in the lookup.  Declared for the neurons whose states are all gates (state k <-> rates
+# 2k, 2k + 1); the others (TC, STN, LeechT/P, FHnode: ion concentrations, GHK currents) are not simulated.
+# iNet = sum of `currents()` in declaration order (pneuron.py:162-166); constants from the neuron files.
+# dt_factor: neuron-specific output time step, in units of DT_EFFECTIVE (`chooseTimeStep`: hh.py:127-129,
+# sweeney.py:105-106, mrg.py:170-172, sundt.py:176-178); spike_mph: spike amplitude threshold (sundt.py:180-182).
+# ---------------------------------------------------------------------------------------------
+_HH = 'gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * n * (Vm - EK)'
+NEURON_SIM = {
+    # cortical.py:96-119,122-200
+    'RS': dict(states=['m', 'h', 'n', 'p'], consts=dict(gNabar=560.0, ENa=50.0, gKdbar=60.0, EK=-90.0, gMbar=0.75,
+                                                       gLeak=0.205, ELeak=-70.3),
+               inet=_HH + ' + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak)'),
+    'FS': dict(states=['m', 'h', 'n', 'p'], consts=dict(gNabar=580.0, ENa=50.0, gKdbar=39.0, EK=-90.0, gMbar=0.787,
+                                                       gLeak=0.38, ELeak=-70.4),
+               inet=_HH + ' + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak)'),
+    # cortical.py:203-300 (iCaT) and :303-401 (iCaL)
+    'LTS': dict(states=['m', 'h', 'n', 'p', 's', 'u'],
+                consts=dict(gNabar=500.0, ENa=50.0, gKdbar=40.0, EK=-90.0, gMbar=0.28, gLeak=0.19, ELeak=-50.0,
+                            gCaTbar=4.0, ECa=120.0),
+                inet=_HH + ' + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak) + gCaTbar * s * s * u * (Vm - ECa)'),
+    'IB': dict(states=['m', 'h', 'n', 'p', 'q', 'r'],
+               consts=dict(gNabar=500.0, ENa=50.0, gKdbar=50.0, EK=-90.0, gMbar=0.3, gLeak=0.1, ELeak=-70.0,
+                           gCaLbar=1.0, ECa=120.0),
+               inet=_HH + ' + gMbar * p * (Vm - EK) + gLeak * (Vm - ELeak) + gCaLbar * q * q * r * (Vm - ECa)'),
+    # thalamic.py:117-179
+    'RE': dict(states=['m', 'h', 'n', 's', 'u'],
+               consts=dict(gNabar=2000.0, ENa=50.0, gKdbar=200.0, EK=-90.0, gCaTbar=30.0, ECa=120.0, gLeak=0.5,
+                           ELeak=-90.0),
+               inet=_HH + ' + gCaTbar * s * s * u * (Vm - ECa) + gLeak * (Vm - ELeak)'),
+    # hh.py:22-29,100-113 and template.py:26-35,94-107
+    'HHseg': dict(dt_factor=1e-1, states=['m', 'h', 'n'], consts=dict(gNabar=1200.0, ENa=50.0, gKdbar=360.0, EK=-77.0, gLeak=3.0,
+                                                     ELeak=-54.3),
+                  inet=_HH + ' + gLeak * (Vm - ELeak)'),
+    'template': dict(states=['m', 'h', 'n'], consts=dict(gNabar=560.0, ENa=50.0, gKdbar=60.0, EK=-90.0, gLeak=0.205,
+                                                        ELeak=-70.3),
+                     inet=_HH + ' + gLeak * (Vm - ELeak)'),
+    # sweeney.py:28-35,84-93
+    'SWnode': dict(dt_factor=1e-2, states=['m', 'h'], consts=dict(gNabar=14450.0, ENa=35.64, gLeak=1280.0, ELeak=-80.01),
+                   inet='gNabar * m * m * h * (Vm - ENa) + gLeak * (Vm - ELeak)'),
+    # mrg.py:37-47,143-162
+    'MRGnode': dict(dt_factor=1e-2, states=['m', 'h', 'p', 's'],
+                    consts=dict(gNafbar=30000.0, gNapbar=100.0, ENa=50.0, gKsbar=800.0, EK=-90.0, gLeak=70.0,
+                                ELeak=-90.0),
+                    inet='gNafbar * m * m * m * h * (Vm - ENa) + gNapbar * p * p * p * (Vm - ENa)'
+                         ' + gKsbar * s * (Vm - EK) + gLeak * (Vm - ELeak)'),
+    # sundt.py:38-52,150-166 (ELeak balances the currents at rest, sundt.py:64-68)
+    'SUseg': dict(dt_factor=1e-2, spike_mph=-8.0e-5, states=['m', 'h', 'n', 'l'],
+                  consts=dict(gNabar=400.0, ENa=55.0, gKdbar=400.0, EK=-90.0, gLeak=1.0, ELeak=-60.069175300110516),
+                  inet='gNabar * m * m * m * h * (Vm - ENa) + gKdbar * n * n * n * l * (Vm - EK)'
+                       ' + gLeak * (Vm - ELeak)'),
+}
+
 NEURON_ORDER = ['RS', 'FS', 'LTS', 'IB', 'RE', 'TC', 'STN', 'FHnode', 'SWnode', 'MRGnode', 'SUseg',
                 'HHseg', 'LeechT', 'LeechP', 'template', 'pas']
 MAX_RATES = 18
@@ -241,6 +297,9 @@ class PointNeuron:
         self.Vm0 = spec['Vm0']
         self.rates = spec_rate_names(name)
         self.neuron_id = NEURON_ORDER.index(name)
+        self.states = list(NEURON_SIM[name]['states']) if name in NEURON_SIM else None
+        self.dt_factor = NEURON_SIM.get(name, {}).get('dt_factor', 1.0)
+        self.spike_mph = NEURON_SIM.get(name, {}).get('spike_mph')
 
     def __repr__(self):
         return f'PointNeuron({self.name})'

@@ -771,3 +771,75 @@ def test_foreign_neuron_rates_are_checked_on_the_device(gpu):
     assert as_point_neuron(Tweaked(1.0)).name == 'HHseg'
     with pytest.raises(ValueError, match='betan'):
         as_point_neuron(Tweaked(1.5))
+
+
+# ---------------------------------------------------------------------------------------------
+# SONIC simulations on the tables
+# ---------------------------------------------------------------------------------------------
+def _sim_goldens():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sonic_sims.json')) as fh:
+        return json.load(fh)['cases']
+
+
+def _fixture_lookup(fname):
+    ps = _ps()
+    g = load_grid(fname)
+    refs = {k: g[k] for k in ('a', 'f', 'A', 'Q', 'fs')}
+    return ps.Lookup(refs, {str(k): g['tab_' + str(k)] for k in g['keys']})
+
+
+def test_sonic_simulations_match_reference(gpu):
+    ''' NeuronalBilayerSonophore.simulate(method='sonic') on the GPU against the reference's own
+        simulate (nbls.py:389-437) run on the SAME reference-built tables, for the ten neurons whose
+        states are all gates: identical sample times and stimulus states, identical spike counts (third
+        parity criterion of north_star), charge / potential / gate trajectories on top of each other
+        (the reference integrates with LSODA at atol = 1.5e-8 on a charge of 1e-3 C/m2, i.e. 1e-5
+        relative: a spike may sit a few microseconds apart). '''
+    ps = _ps()
+    cases = _sim_goldens()
+    assert len({c['neuron'] for c in cases}) >= 10
+    lookups = {}
+    for c in cases:
+        lkp = lookups.setdefault(c['fixture'], _fixture_lookup(c['fixture']))
+        nbls = ps.NeuronalBilayerSonophore(c['a'], ps.getPointNeuron(c['neuron']))
+        pp = ps.PulsedProtocol(c['tstim'], c['toffset'], PRF=c['PRF'], DC=c['DC'])
+        data, meta = nbls.simulate(ps.AcousticDrive(c['f'], c['A']), pp, fs=1.0, method='sonic', lookup=lkp)
+        label = (c['neuron'], c['A'], c['PRF'], c['DC'])
+        assert list(data.columns) == c['columns'] + ['Z', 'ng'], label
+        assert len(data) == c['nsamples'], label
+        np.testing.assert_array_equal(data['t'].values[:8], c['t_all_head'])
+        assert data['t'].values[-1] == c['t_last'] and data['stimstate'].values.sum() == c['stim_sum']
+        assert nbls.getNSpikes(data) == c['nspikes'], label
+        step = c['step']
+        for col in c['columns']:
+            ref = np.array(c['samples'][col])
+            mine = data[col].values[::step]
+            if col in ('t', 'stimstate'):
+                np.testing.assert_array_equal(mine, ref)
+                continue
+            scale = max(np.ptp(ref), 1e-12)
+            dev = np.abs(mine - ref) / scale
+            assert np.median(dev) <= 2e-4, (label, col, float(np.median(dev)))
+            assert np.mean(dev > 2e-2) <= 0.02, (label, col, float(np.mean(dev > 2e-2)))     # samples on a spike flank
+            assert abs(data[col].values[-1] - c['final'][col]) <= 2e-3 * scale + 1e-12, (label, col)
+
+
+def test_sonic_simulation_batch_and_errors(gpu):
+    ps = _ps()
+    lkp = _fixture_lookup('c1_RS_32nm_500kHz.npz')
+    nbls = ps.NeuronalBilayerSonophore(32e-9, ps.getPointNeuron('RS'))
+    pp = ps.PulsedProtocol(100e-3, 50e-3)
+    amps = [20e3, 50e3, 100e3, 300e3, 600e3]
+    batch = nbls.simulate_batch(500e3, amps, pp, lookup=lkp)
+    counts = [nbls.getNSpikes(d) for d in batch]
+    assert counts == [0, 12, 35, 57, 68]                  # the reference's counts on the same table
+    one, _ = nbls.simulate(ps.AcousticDrive(500e3, 100e3), pp, lookup=lkp)
+    np.testing.assert_array_equal(one['Qm'].values, batch[2]['Qm'].values)
+    # an amplitude outside the table, an unsupported neuron, a method that needs no table
+    with pytest.raises(ValueError, match='out of'):
+        nbls.simulate(ps.AcousticDrive(500e3, 700e3), pp, lookup=lkp)
+    with pytest.raises(ValueError, match='method'):
+        nbls.simulate(ps.AcousticDrive(500e3, 100e3), pp, method='full', lookup=lkp)
+    with pytest.raises(NotImplementedError):
+        ps.NeuronalBilayerSonophore(32e-9, ps.getPointNeuron('STN')).simulate_batch(500e3, [1e5], pp, lookup=lkp)

@@ -392,3 +392,56 @@ def test_foreign_point_neuron_is_verified_not_trusted_by_name():
     f.rates = f.rates[:6]
     with pytest.raises(ValueError, match='rate constants'):
         as_point_neuron(f)
+
+
+# ---------------------------------------------------------------------------------------------
+# table consumption: lookup projections, pulsing protocol, sample plan of the solver
+# ---------------------------------------------------------------------------------------------
+def test_lookup_projection_is_linear_interpolation():
+    from scipy.interpolate import interp1d
+    rng = np.random.default_rng(4)
+    refs = {'a': np.array([16e-9, 32e-9]), 'A': np.array([0., 1e4, 5e4, 3e5]), 'Q': np.linspace(-1e-3, 5e-4, 7)}
+    tabs = {'V': rng.normal(size=(2, 4, 7)), 'alpham': rng.uniform(size=(2, 4, 7))}
+    lkp = ps.Lookup(refs, tabs)
+    p = lkp.project('A', 2.3e4)
+    assert p.inputs == ['a', 'Q'] and p['V'].shape == (2, 7)
+    np.testing.assert_allclose(p['V'], interp1d(refs['A'], tabs['V'], axis=1)(2.3e4), rtol=1e-14)
+    p2 = lkp.project('A', np.array([0., 2e5]))
+    assert p2.inputs == ['a', 'A', 'Q'] and p2['alpham'].shape == (2, 2, 7)
+    np.testing.assert_allclose(p2['alpham'], interp1d(refs['A'], tabs['alpham'], axis=1)([0., 2e5]), rtol=1e-14)
+    one = lkp.projectN({'a': 32e-9, 'A': 5e4})
+    assert one.inputs == ['Q'] and one.ndims == 1
+    np.testing.assert_allclose(one['V'], tabs['V'][1, 2], rtol=1e-14)
+    np.testing.assert_allclose(one.interpolate1D(-2e-4)['V'], np.interp(-2e-4, refs['Q'], tabs['V'][1, 2]))
+    with pytest.raises(ValueError, match='out of'):
+        lkp.project('A', 4e5)
+    with pytest.raises(ValueError, match='out of'):
+        one.interpolate1D(6e-4)
+    assert ps.Lookup({'f': np.array([5e5]), 'Q': refs['Q']}, {'V': tabs['V'][:1, 0]}).project('f', 5e5)['V'].shape == (7,)
+
+
+def test_pulsed_protocol_and_sample_plan_match_reference():
+    ''' Transition events (protocols.py:372-391) and the sample times / stimulus states of
+        EventDrivenSolver.solve (solvers.py:445-478), against the reference's simulation outputs. '''
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sonic_sims.json')) as fh:
+        cases = json.load(fh)['cases']
+    seen = set()
+    for c in cases:
+        dtf = ps.getPointNeuron(c['neuron']).dt_factor       # neuron-specific output step (chooseTimeStep)
+        key = (c['tstim'], c['toffset'], c['PRF'], c['DC'], dtf)
+        if key in seen or 'error' in c:
+            continue
+        seen.add(key)
+        pp = ps.PulsedProtocol(c['tstim'], c['toffset'], PRF=c['PRF'], DC=c['DC'])
+        assert pp.tstop == c['tstim'] + c['toffset']
+        t, x = ps.NeuronalBilayerSonophore._sample_plan(pp.stimEvents(), pp.tstop, ps.DT_EFFECTIVE * dtf)
+        assert t.size == c['nsamples'] and t[-1] == c['t_last'] and x.sum() == c['stim_sum']
+        np.testing.assert_array_equal(t[:8], c['t_all_head'])
+        np.testing.assert_array_equal(t[::c['step']], c['samples']['t'])
+        np.testing.assert_array_equal(x[::c['step']], c['samples']['stimstate'])
+    assert len(seen) >= 5
+    ev = ps.PulsedProtocol(0.1, 0.05, PRF=100., DC=0.5).stimEvents()
+    assert len(ev) == 20 and ev[0] == (0.0, 1.0) and ev[1] == (0.005, 0.0)
+    with pytest.raises(ValueError):
+        ps.PulsedProtocol(0.1, 0.05, PRF=5., DC=0.5)
