@@ -231,7 +231,8 @@ def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None, device=0):
                         "entry's own deviation under +-2 ulp re-runs of the reference)"}
 
     def variants(stem):
-        return [np.load(os.path.join(gold, stem + t)) for t in ('_ulp_up.npz', '_ulp_dn.npz')
+        return [np.load(os.path.join(gold, stem + t))
+                for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz', '_ulp_up3.npz', '_ulp_dn3.npz')
                 if os.path.isfile(os.path.join(gold, stem + t))]
 
     g = np.load(os.path.join(gold, 'c1_RS_32nm_500kHz.npz'))
@@ -241,7 +242,7 @@ def live_parity(ps, lkp_c2=None, info_c2=None, w_c2=None, device=0):
                                       return_info=True, loglevel=10, device=device, shard=False)
     out['c1_full_1000_points'] = parity_stats(lkp.tables, info['ncycles'], g, variants('c1_RS_32nm_500kHz'), keys)
     big = os.path.join(gold, 'c2_RS_big.npz')
-    if lkp_c2 is not None and os.path.isfile(big) and len(variants('c2_RS_big')) == 2:
+    if lkp_c2 is not None and os.path.isfile(big) and len(variants('c2_RS_big')) >= 2:
         g = np.load(big)
         iQ = [int(np.argmin(np.abs(w_c2['Q'] - x))) for x in g['Q']]
         if np.array_equal(w_c2['Q'][iQ], g['Q']) and np.array_equal(w_c2['A'], g['A']):

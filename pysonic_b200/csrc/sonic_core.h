@@ -368,12 +368,16 @@ SONIC_HD double sonic_charge_sample(double q0, int nov, const double* ov, int j)
 // Index of the charge sample in force at time t: int((t mod T) / dt), T = 1 / f, dt = T / 1000
 // (bls.py:766-768), and the matching electrical pressure factor.
 
-// d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2).  The heuristics
-// only steer the step size (the result is clipped, thresholded at 10 % and multiplied by safety
-// factors), so on the device the power goes through the single-precision log2/exp2 units
-// (relative error ~1e-7), with the binary exponent of d split off in double precision so that
-// the whole double range is covered.  A dozen instructions instead of ~150, at seven call sites.
-SONIC_HD double sonic_powr(double d, double ex) {
+// d^ex for the step-size heuristics of the integrator (d >= 0, 0 < ex <= 1/2), in two accuracies on the
+// device.  Round 1 took every power through the single-precision log2 / exp2 units (relative error
+// ~1e-7, a dozen instructions): the heuristics "only steer the step size".  But the reference's results
+// carry its integration error (up to 9e-5 of the converged solution), which depends on the exact sequence
+// of step sizes: with single-precision powers the steps drift from the reference's, and reproducible
+// points such as 64 nm / 20 kHz / 85 kPa end up 1.8e-4 away from it, against 5e-6 with double-precision
+// powers.  So: wherever a power SETS the step size (order / step selection, a method switch that is
+// actually made) it is computed to double precision (`sonic_powr`); the per-step test "would the other method allow a five times larger step?" only compares
+// candidates and keeps the fast form (`sonic_powr_fast`).  The CPU build uses pow() for both.
+SONIC_HD double sonic_powr_fast(double d, double ex) {
 #if defined(__CUDA_ARCH__)
     if (!(d > 0.0)) return 0.0;
     const int hi = __double2hiint(d);
@@ -386,16 +390,55 @@ SONIC_HD double sonic_powr(double d, double ex) {
 #endif
 }
 
-// (d * c)^ex where d^ex may already be at hand (`*pd`, NaN = not yet) and ce = c^ex is tabulated:
-// on the device the power of the local error estimate is computed once per step and shared by
-// every step-size candidate derived from it; the host build takes the power of the product.
-SONIC_HD double sonic_powr_scaled(double d, double c, double ce, double ex, double* pd) {
+// d^(1/l), l = 2 ... 14 (every exponent of the heuristics is the reciprocal of an order + 0, 1 or 2), to a
+// few ulp on the device: the single-precision value y (relative error e0 ~ 1e-7) is corrected with one
+// step of the third-order iteration for the l-th root, y (1 + e / l (1 - (l - 1) e / (2 l))) with
+// e = d / y^l - 1, which leaves an error of order e0^3.
+SONIC_HD double sonic_powr(double d, double ex, int l) {
+#if defined(__CUDA_ARCH__)
+    const double y = sonic_powr_fast(d, ex);
+    if (!(y > 0.0)) return 0.0;
+    double p = 1.0, b = y;                 // p = y^l by squaring
+    int k = l;
+#pragma unroll 1
+    while (k > 0) {
+        if (k & 1) p *= b;
+        b *= b;
+        k >>= 1;
+    }
+    const double e = (d - p) * sonic_rcp(p);
+    const double il = 1.0 / (double)l;
+    return fma(y * (e * il), fma(-0.5 * (double)(l - 1) * il, e, 1.0), y);
+#else
+    (void)l;
+    return pow(d, ex);
+#endif
+}
+
+// The power of the local error estimate, dsm^(1 / (nq + 1)), is needed by the method-switch test and by
+// the order selection of the same step: it is computed once per accuracy (NaN = not yet).
+struct SonicStepCtx {
+    double pw_fast, pw_exact;
+};
+
+SONIC_HD double sonic_dsm_power(double dsm, double ex, int l, SonicStepCtx* c, bool exact) {
+    if (exact) {
+        if (c->pw_exact != c->pw_exact) c->pw_exact = sonic_powr(dsm, ex, l);
+        return c->pw_exact;
+    }
+    if (c->pw_exact == c->pw_exact) return c->pw_exact;
+    if (c->pw_fast != c->pw_fast) c->pw_fast = sonic_powr_fast(dsm, ex);
+    return c->pw_fast;
+}
+
+// (d * c)^ex with d^ex from the shared power above and ce = c^ex tabulated; the host build takes the
+// power of the product, as the original does.
+SONIC_HD double sonic_powr_scaled(double d, double c, double ce, double ex, int l, SonicStepCtx* ctx, bool exact) {
 #if defined(__CUDA_ARCH__)
     (void)c;
-    if (*pd != *pd) *pd = sonic_powr(d, ex);
-    return *pd * ce;
+    return sonic_dsm_power(d, ex, l, ctx, exact) * ce;
 #else
-    (void)ce; (void)pd;
+    (void)ce; (void)ctx; (void)exact; (void)l;
     return pow(d * c, ex);
 #endif
 }
@@ -964,34 +1007,30 @@ SONIC_HD void sonic_fail(SonicLane& s, unsigned bit) {
     s.phase = PH_DONE;
 }
 
-// Choose the next order/step after a success (ialth == 0, iredo = 0) or an error-test failure
-// (iredo = 2).  Returns true if the step must be redone (predict again).
 // Step-size candidate at the current order from the local error estimate dsm:
-// 1 / (1.2 dsm^(1/l) + 1.2e-6).  Needed by both the method-switch test and the order
-// selection of the same step, so it is computed once (NaN = not yet) together with log(dsm).
-struct SonicStepCtx {
-    double rhsm0;
-    double lds;
-};
-
-SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepCtx* c) {
-    if (c->rhsm0 != c->rhsm0) {
-        const double exsm = T->rk[s.nq + 1];
-        c->rhsm0 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, 1.0, 1.0, exsm, &c->lds) + 0.0000012);
-    }
-    return c->rhsm0;
+// 1 / (1.2 dsm^(1/l) + 1.2e-6).
+SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepCtx* c, bool exact) {
+    const double exsm = T->rk[s.nq + 1];
+#if defined(__CUDA_ARCH__)
+    return sonic_rcp(1.2 * sonic_dsm_power(s.dsm, exsm, s.nq + 1, c, exact) + 0.0000012);
+#else
+    (void)c; (void)exact;
+    return sonic_rcp(1.2 * pow(s.dsm * 1.0, exsm) + 0.0000012);
+#endif
 }
 
+// Choose the next order/step after a success (ialth == 0, iredo = 0) or an error-test failure
+// (iredo = 2).  Returns true if the step must be redone (predict again).  Sets the step size: exact powers.
 SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* T, double rhup,
                            int iredo, SonicStepCtx* ctx, SonicRescaleReq& rq) {
     const int l = s.nq + 1;
     const int lmax = SONIC_LMAX(s);
-    double rhsm = sonic_rhsm0(s, T, ctx);
+    double rhsm = sonic_rhsm0(s, T, ctx, true);
     double rhdn = 0.0;
     if (s.nq != 1) {
         const double ddn = SONIC_QUOT(sonic_mnorm_col(H, s.nq, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
         const double exdn = T->rk[s.nq];
-        rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn) + 0.0000013);
+        rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn, s.nq) + 0.0000013);
     }
     double pdh = 0.0;
     if (s.meth == 1) {
@@ -1049,62 +1088,75 @@ SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* 
     return iredo != 0;
 }
 
-// Consider switching Adams <-> BDF after a successful step.  Returns true if a switch was
-// made (history rescaled, step finished).
-SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicTables* T,
-                                  SonicStepCtx* ctx, SonicRescaleReq& rq) {
+// Consider switching Adams <-> BDF after a successful step: the decision and, if a switch is to be made,
+// the new order and step-size ratio.  No side effect.
+SONIC_HD bool sonic_method_switch_decide(const SonicLane& s, const SonicTables* T, SonicStepCtx* ctx, bool exact,
+                                         int* nq_new, double* rh_new) {
     const double exsm = T->rk[s.nq + 1];
     if (s.meth == 1) {
         if (s.nq > 5) return false;
-        double rh2;
-        int nqm2;
         if (s.dsm > 100.0 * s.pnorm * SONIC_UROUND && s.pdest != 0.0) {
-            double rh1 = sonic_rhsm0(s, T, ctx);
+            double rh1 = sonic_rhsm0(s, T, ctx, exact);
             double rh1it = 2.0 * rh1;
             const double pdh = s.pdlast * fabs(s.h);
             if (pdh * rh1 > 0.00001) rh1it = sonic_div(T->sm1[s.nq - 1], pdh);
             rh1 = fmin(rh1, rh1it);
             // nq <= 5 = MXORDS here, so the "reduce to MXORDS" branch cannot be taken
             const double c12 = T->c12[s.nq - 1];
-            rh2 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c12, T->c12e[s.nq - 1], exsm, &ctx->lds) +
-                            0.0000012);
-            nqm2 = s.nq;
+            const double rh2 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c12, T->c12e[s.nq - 1], exsm, s.nq + 1, ctx, exact) +
+                                         0.0000012);
             if (rh2 < 5.0 * rh1) return false;
+            *rh_new = rh2;
+            *nq_new = s.nq;
         } else {
             if (s.irflag == 0) return false;
-            rh2 = 2.0;
-            nqm2 = s.nq < SONIC_MXORDS ? s.nq : SONIC_MXORDS;
+            *rh_new = 2.0;
+            *nq_new = s.nq < SONIC_MXORDS ? s.nq : SONIC_MXORDS;
         }
-        s.icount = 20;
-        s.meth = 2;
-        s.miter = 2;
-        s.pdlast = 0.0;
-        s.nq = nqm2;
-        rq.pending = true; rq.rh = rh2; rq.rmax10 = true;
         return true;
     }
     // currently BDF (nq <= 5 <= MXORDN): consider Adams at the same order
     const double c21 = T->c21[s.nq - 1];
     double dm1 = s.dsm * c21;
-    double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->c21e[s.nq - 1], exsm, &ctx->lds) +
-                           0.0000012);
-    const int nqm1 = s.nq;
+    double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->c21e[s.nq - 1], exsm, s.nq + 1, ctx, exact) + 0.0000012);
     const double exm1 = exsm;
     double rh1it = 2.0 * rh1;
     const double pdh = s.pdnorm * fabs(s.h);
-    if (pdh * rh1 > 0.00001) rh1it = sonic_div(T->sm1[nqm1 - 1], pdh);
+    if (pdh * rh1 > 0.00001) rh1it = sonic_div(T->sm1[s.nq - 1], pdh);
     rh1 = fmin(rh1, rh1it);
-    const double rh2 = sonic_rhsm0(s, T, ctx);
+    const double rh2 = sonic_rhsm0(s, T, ctx, exact);
     if (rh1 * 5.0 < 5.0 * rh2) return false;
     const double alpha = fmax(0.001, rh1);
-    dm1 = sonic_powr(alpha, exm1) * dm1;
+    dm1 = (exact ? sonic_powr(alpha, exm1, s.nq + 1) : sonic_powr_fast(alpha, exm1)) * dm1;
     if (dm1 <= 1000.0 * SONIC_UROUND * s.pnorm) return false;
+    *rh_new = rh1;
+    *nq_new = s.nq;
+    return true;
+}
+
+// Returns true if a switch was made (history rescale filed, step finished).  The per-step test runs on
+// the fast powers; a switch that it calls for is re-decided, and its step-size ratio computed, with the
+// exact ones (the CPU build has one accuracy: decided once).
+SONIC_HD bool sonic_method_switch(SonicLane& s, const SonicHist& H, const SonicTables* T,
+                                  SonicStepCtx* ctx, SonicRescaleReq& rq) {
+    (void)H;
+    int nqm = s.nq;
+    double rh = 1.0;
+#if defined(__CUDA_ARCH__)
+    if (!sonic_method_switch_decide(s, T, ctx, false, &nqm, &rh)) return false;
+#endif
+    if (!sonic_method_switch_decide(s, T, ctx, true, &nqm, &rh)) return false;
     s.icount = 20;
-    s.meth = 1;
-    s.miter = 0;
+    if (s.meth == 1) {
+        s.meth = 2;
+        s.miter = 2;
+    } else {
+        s.meth = 1;
+        s.miter = 0;
+    }
     s.pdlast = 0.0;
-    s.nq = nqm1;
-    rq.pending = true; rq.rh = rh1; rq.rmax10 = true;
+    s.nq = nqm;
+    rq.pending = true; rq.rh = rh; rq.rmax10 = true;
     return true;
 }
 
@@ -1382,7 +1434,7 @@ SONIC_HD void sonic_after_accept(SonicLane& s, const SonicHist& H, const SonicTa
                                             s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
             const double dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
             const double exup = T->rk[l + 1];
-            sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup) + 0.0000014);
+            sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup, l + 1) + 0.0000014);
         }
         sel_mode = 1;
     } else if (s.ialth <= 1 && l != lmax) {
@@ -1543,7 +1595,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     int sel_mode = 0;          // 1 = order/step selection after a success, 2 = after a failure
     double sel_rhup = 0.0;
     SonicStepCtx ctx;
-    ctx.rhsm0 = ctx.lds = NAN;
+    ctx.pw_fast = ctx.pw_exact = NAN;
     SonicRescaleReq rq;
     rq.pending = false; rq.rmax10 = false; rq.rh = 1.0;
     if (cf_retract || err_failed) sonic_retract(s, H, cf_retract, do_predict, sel_mode, rq);
@@ -1624,7 +1676,7 @@ SONIC_HD void sonic_tick_lone(SonicLane& s, const SonicHist& H, const SonicTable
     }
     if (!converged && !corr_failed) return;           // one more corrector iterate at (tn, y)
     SonicStepCtx ctx;
-    ctx.rhsm0 = ctx.lds = NAN;
+    ctx.pw_fast = ctx.pw_exact = NAN;
     bool failed = corr_failed;                        // a path that retracts the step
     if (corr_failed) {
         if (s.miter != 0 && s.jcur != 1) {

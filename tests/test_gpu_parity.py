@@ -244,7 +244,7 @@ def _need(fname):
 
 def _variants(fname):
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-    return [load_grid(fname.replace('.npz', t)) for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz')
+    return [load_grid(fname.replace('.npz', t)) for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz', '_ulp_up3.npz', '_ulp_dn3.npz')
             if os.path.isfile(os.path.join(here, fname.replace('.npz', t)))]
 
 

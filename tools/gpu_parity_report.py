@@ -24,7 +24,7 @@ out = {'tolerance': 'V and rates within 1e-4 relative (1e-9 absolute); per-entry
 stems = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, 'c?_*.npz')) if '_ulp_' not in p)
 for stem in stems:
     g = np.load(os.path.join(GOLD, stem + '.npz'))
-    variants = [np.load(os.path.join(GOLD, stem + t)) for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz')
+    variants = [np.load(os.path.join(GOLD, stem + t)) for t in ('_ulp_up.npz', '_ulp_dn.npz', '_ulp_up2.npz', '_ulp_dn2.npz', '_ulp_up3.npz', '_ulp_dn3.npz')
                 if os.path.isfile(os.path.join(GOLD, stem + t))]
     if len(variants) < 2:
         continue
