@@ -40,7 +40,15 @@ for name, runs in [('FS', STD_RUNS), ('LTS', STD_RUNS), ('IB', STD_RUNS), ('RE',
     if not os.path.isfile(os.path.join(HERE, fname)):
         mg._grid_to_npz(fname, name, [32e-9], [500e3], SIM_AMPS, mg.default_charges(name), [1.0])
     CASES.append((fname, 32e-9, 500e3, runs))
+# reference-built tables only (states that are not gates: simulated by the reference alone, for the spike-count
+# parity of engine-built tables, tools/spike_parity.py)
+for name in ('STN', 'TC'):
+    fname = f'sim_tab_{name}.npz'
+    if not os.path.isfile(os.path.join(HERE, fname)):
+        mg._grid_to_npz(fname, name, [32e-9], [500e3], SIM_AMPS, mg.default_charges(name), [1.0])
 
+if '--tables-only' in sys.argv:
+    sys.exit(0)
 out = {'cases': []}
 for fixture, a, f, runs in CASES:
     g = np.load(os.path.join(HERE, fixture))

@@ -5,11 +5,10 @@
 
     Build container only (imports the unmodified reference through tests/golden/_refshim.py).
 
-        python tools/spike_parity.py <engine_table.pkl> [out.json]
+        python tools/spike_parity.py gpurun_out/tables [out.json]
 
-    <engine_table.pkl>: BASELINE config 1 (RS, 32 nm, 500 kHz, 20 A x 50 Q, fs = 1) written by
-    `pysonic_b200` on the GPU box (tools/gpu_make_c1_table.py), brought back in gpurun_out/.
-    The reference-built table of the same grid is tests/golden/c1_RS_32nm_500kHz.npz.
+    <dir>/<neuron>.pkl: tables written by `pysonic_b200` on the GPU box (tools/gpu_make_sim_tables.py) on the grids
+    of the reference-built fixtures tests/golden/c1_RS_32nm_500kHz.npz (RS) and tests/golden/sim_tab_<neuron>.npz.
 '''
 import json
 import os
@@ -21,7 +20,8 @@ import tempfile
 import numpy as np
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, GOLD)
 from _refshim import load_reference  # noqa: E402
 
 load_reference()
@@ -29,49 +29,62 @@ import PySONIC.core.nbls as ref_nbls  # noqa: E402
 from PySONIC.core import NeuronalBilayerSonophore, AcousticDrive, PulsedProtocol  # noqa: E402
 from PySONIC.neurons import getPointNeuron  # noqa: E402
 
+PROTOCOLS = {'default': (100e-3, 50e-3), 'SWnode': (3e-3, 5e-3), 'MRGnode': (3e-3, 5e-3), 'SUseg': (3e-3, 5e-3)}
 
-def spikes_with_table(path, amps):
+
+def spikes_with_table(name, path, amps):
     d = tempfile.mkdtemp()
     try:
-        shutil.copy(path, os.path.join(d, 'RS_lookups_fs1.00.pkl'))
+        nbls = NeuronalBilayerSonophore(32e-9, getPointNeuron(name))
+        shutil.copy(path, os.path.join(d, nbls.getLookupFileName(fs=1.0)))
         ref_nbls.LOOKUP_DIR = d
-        nbls = NeuronalBilayerSonophore(32e-9, getPointNeuron('RS'))
-        pp = PulsedProtocol(100e-3, 50e-3)
+        pp = PulsedProtocol(*PROTOCOLS.get(name, PROTOCOLS['default']))
         out = []
         for A in amps:
-            data, meta = nbls.simulate(AcousticDrive(500e3, A), pp, method='sonic')
-            out.append(int(nbls.pneuron.getNSpikes(data)))
+            try:
+                data, meta = nbls.simulate(AcousticDrive(500e3, A), pp, method='sonic')
+                out.append(int(nbls.pneuron.getNSpikes(data)))
+            except ValueError:          # the charge leaves the tabulated range
+                out.append(None)
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
 
-def golden_table_pickle(path):
-    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_RS_32nm_500kHz.npz'))
+def fixture_pickle(fixture, path):
+    g = np.load(os.path.join(GOLD, fixture))
     refs = {k: g[k] for k in ('a', 'f', 'A', 'Q', 'fs')}
     tables = {str(k): g['tab_' + str(k)] for k in g['keys']}
     tables['tcomp'] = np.moveaxis(np.array([g['tcomp']]), 0, -1)
     with open(path, 'wb') as fh:
         pickle.dump({'refs': refs, 'tables': tables}, fh)
+    return refs['A']
 
 
 def main():
-    engine = sys.argv[1]
-    amps = [20e3, 50e3, 100e3, 200e3, 400e3, 600e3]
+    tdir = sys.argv[1]
     tmp = tempfile.mkdtemp()
-    refp = os.path.join(tmp, 'ref.pkl')
-    golden_table_pickle(refp)
-    n_ref = spikes_with_table(refp, amps)
-    n_eng = spikes_with_table(engine, amps)
-    res = {'neuron': 'RS', 'a': 32e-9, 'f': 500e3, 'protocol': 'PulsedProtocol(100 ms, 50 ms)',
-           'amplitudes_Pa': amps, 'spikes_reference_table': n_ref, 'spikes_engine_table': n_eng,
-           'identical': n_ref == n_eng, 'engine_table': os.path.basename(engine)}
-    print(json.dumps(res))
+    res = []
+    for fn in sorted(os.listdir(tdir)):
+        name = fn[:-4]
+        fixture = 'c1_RS_32nm_500kHz.npz' if name == 'RS' else f'sim_tab_{name}.npz'
+        if not os.path.isfile(os.path.join(GOLD, fixture)):
+            continue
+        refp = os.path.join(tmp, f'{name}_ref.pkl')
+        Aref = fixture_pickle(fixture, refp)
+        amps = [20e3, 50e3, 100e3, 200e3, 400e3, 600e3] if name == 'RS' else [30e3, 50e3, 75e3, 100e3, 200e3, 300e3]
+        amps = [A for A in amps if A <= Aref.max()]
+        n_ref = spikes_with_table(name, refp, amps)
+        n_eng = spikes_with_table(name, os.path.join(tdir, fn), amps)
+        r = {'neuron': name, 'a': 32e-9, 'f': 500e3, 'fixture': fixture, 'amplitudes_Pa': amps,
+             'spikes_reference_table': n_ref, 'spikes_engine_table': n_eng, 'identical': n_ref == n_eng}
+        print(json.dumps(r), flush=True)
+        res.append(r)
     if len(sys.argv) > 2:
         with open(sys.argv[2], 'w') as fh:
             json.dump(res, fh, indent=1)
     shutil.rmtree(tmp, ignore_errors=True)
-    sys.exit(0 if res['identical'] else 1)
+    sys.exit(0 if all(r['identical'] for r in res) else 1)
 
 
 if __name__ == '__main__':
