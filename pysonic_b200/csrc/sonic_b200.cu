@@ -284,11 +284,11 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     }
 }
 
-// Fused cycle averaging.  One warp per output point; the point's capacitance profile is staged in
-// shared memory and reused for every coverage fraction.  A block works on a tile of `pt_tile`
-// consecutive output points x `j_tile` coverage fractions, collects the results of the tile in
-// shared memory and writes every table's contiguous run of the tile (out is [table][point][fs])
-// with consecutive threads on consecutive addresses.
+// Fused cycle averaging.  A warp works through a contiguous range of output points; the capacitance
+// profile of the current point is staged in shared memory and reused for every coverage fraction.
+// Every table of the output is laid out [point][fs], so the (point, fs) entries a warp produces one
+// after the other are consecutive in memory: lane k keeps the results of the k-th entry of the current
+// run of 32 in registers, and a full run is written with one coalesced 256-byte store per table.
 struct SonicAvgArgs {
     const double* zbuf;        // [n_traj][1000] last-cycle deflections
     const int* ia_out;         // [n_out_all] radius entry of every output point (its own Cm0)
@@ -301,100 +301,101 @@ struct SonicAvgArgs {
     const int* sel;            // [n] output points of this launch (one neuron of a multi-neuron plan), or null
     double* out;               // [nvar][n][nfs]
     long long n;
-    int nfs, nov, pt_tile, j_tile;
+    int nfs, nov, pts_per_chunk;
 };
 
-template <int NID>
+template <int NID, bool OVT>
 __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(SonicAvgArgs a) {
     constexpr int NR = SonicRates<NID>::N;
-    constexpr int NV = 1 + 2 * SONIC_MAX_OVERTONES + NR;
-    extern __shared__ double avg_s[];      // [SONIC_AVG_WARPS][1000] capacitance | [nvar][tile] results
+    constexpr int MOV = OVT ? SONIC_MAX_OVERTONES : 0;      // overtone slots (none in the common instantiation)
+    constexpr int NV = 1 + 2 * MOV + NR;
+    __shared__ double cm_s[SONIC_AVG_WARPS][SONIC_NPC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nov = a.nov, nfs = a.nfs;
+    const int nov = OVT ? a.nov : 0, nfs = a.nfs;
     const int nvar = 1 + 2 * nov + NR;          // V, (A_Vk, phi_Vk) per overtone, rates
-    const int PT = a.pt_tile, JT = a.j_tile, TILE = PT * JT;
-    double* cm = avg_s + warp * SONIC_NPC;
-    double* res = avg_s + SONIC_AVG_WARPS * SONIC_NPC;
+    double* cm = cm_s[warp];
     const long long n = a.n;
-    const long long ntiles = (n + PT - 1) / PT;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long pt0 = tile * PT;
-        const int npt = (int)((n - pt0 < PT) ? (n - pt0) : PT);
-        for (int j0 = 0; j0 < nfs; j0 += JT) {
-            const int nj = (nfs - j0 < JT) ? (nfs - j0) : JT;
-            for (int pl = warp; pl < npt; pl += SONIC_AVG_WARPS) {
-                const long long pt = pt0 + pl;                      // output point of this launch
-                const long long g = a.sel ? a.sel[pt] : pt;         // ... among all output points of the plan
-                const long long u = a.umap ? a.umap[g] : g;         // trajectory the point reads
-                const SonicBls b = a.radii[a.ia_out[g]];
-                const double a2 = b.a * b.a;
-                const double q0 = a.Q[g];
-                const double* ovp = nov ? a.ov + (size_t)u * 2 * nov : nullptr;
-                const bool bad = (a.status[u] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
-                                                 SONIC_ST_TOLSF)) != 0;
-                if (j0 == 0) {
-                    // (several points per warp only occur with a single j tile, see the host side)
-                    const double* z = a.zbuf + u * SONIC_NPC;
-                    __syncwarp();
-                    for (int k = lane; k < SONIC_NPC; k += 32) cm[k] = sonic_capacitance(a2, b.Delta, b.Cm0, z[k]);
-                    __syncwarp();
-                }
-                for (int jj = 0; jj < nj; jj++) {
-                    const double x = a.fs[j0 + jj];
-                    double acc[NV];
+    const long long nchunks = (n + a.pts_per_chunk - 1) / a.pts_per_chunk;
+    const long long nwarps = (long long)gridDim.x * SONIC_AVG_WARPS;
+    for (long long chunk = (long long)blockIdx.x * SONIC_AVG_WARPS + warp; chunk < nchunks; chunk += nwarps) {
+        const long long p_first = chunk * a.pts_per_chunk;
+        const long long p_last = (p_first + a.pts_per_chunk < n) ? p_first + a.pts_per_chunk : n;
+        long long e_run = p_first * nfs;        // first entry (point * nfs + fs index) of the current run
+        int fill = 0;                           // entries of the run computed so far
+        double keep[NV];                        // this lane's entry of the run, one value per table
 #pragma unroll
-                    for (int v = 0; v < NV; v++) acc[v] = 0.0;
-                    for (int k = lane; k < SONIC_NPC; k += 32) {
-                        // imposed charge of sample k (constant without overtones, nbls.py:169-178)
-                        const double q = nov ? sonic_charge_sample(q0, nov, ovp, k) : q0;
-                        // spatial average of the capacitance, then membrane potential in mV
-                        const double vm = q / (x * cm[k] + (1 - x) * b.Cm0) * 1e3;   // nbls.py:148-151,188
-                        double r[NR > 0 ? NR : 1];
-                        SonicRates<NID>::eval(vm, r);
-                        acc[0] += vm;
-                        // Fourier coefficients of the potential, rfft(Vm)[m] (nbls.py:194-201)
-                        for (int m = 1; m <= nov; m++) {
-                            double sn, cs;
-                            sincospi((double)((2 * m * k) % (2 * SONIC_NPC)) * (1.0 / SONIC_NPC), &sn, &cs);
-                            acc[2 * m - 1] += vm * cs;
-                            acc[2 * m] -= vm * sn;
-                        }
+        for (int v = 0; v < NV; v++) keep[v] = 0.0;
+        for (long long pt = p_first; pt < p_last; pt++) {
+            const long long g = a.sel ? a.sel[pt] : pt;         // among all output points of the plan
+            const long long u = a.umap ? a.umap[g] : g;         // trajectory the point reads
+            const SonicBls b = a.radii[a.ia_out[g]];
+            const double a2 = b.a * b.a;
+            const double q0 = a.Q[g];
+            const double* ovp = nov ? a.ov + (size_t)u * 2 * nov : nullptr;
+            const bool bad = (a.status[u] & (SONIC_ST_Z0FAIL | SONIC_ST_STEPFAIL | SONIC_ST_MXSTEP |
+                                             SONIC_ST_TOLSF)) != 0;
+            const double* z = a.zbuf + u * SONIC_NPC;
+            __syncwarp();
+            for (int k = lane; k < SONIC_NPC; k += 32) cm[k] = sonic_capacitance(a2, b.Delta, b.Cm0, z[k]);
+            __syncwarp();
+            for (int j = 0; j < nfs; j++) {
+                const double x = a.fs[j];
+                double acc[NV];
 #pragma unroll
-                        for (int v = 0; v < NR; v++) acc[1 + 2 * SONIC_MAX_OVERTONES + v] += r[v];
-                    }
-#pragma unroll
-                    for (int v = 0; v < NV; v++) {
-                        double t = acc[v];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                        acc[v] = t * (1.0 / (double)SONIC_NPC);
-                    }
-                    // amplitude-phase form of the overtone coefficients
+                for (int v = 0; v < NV; v++) acc[v] = 0.0;
+                for (int k = lane; k < SONIC_NPC; k += 32) {
+                    // imposed charge of sample k (constant without overtones, nbls.py:169-178)
+                    const double q = nov ? sonic_charge_sample(q0, nov, ovp, k) : q0;
+                    // spatial average of the capacitance, then membrane potential in mV
+                    const double vm = q / (x * cm[k] + (1 - x) * b.Cm0) * 1e3;   // nbls.py:148-151,188
+                    double r[NR > 0 ? NR : 1];
+                    SonicRates<NID>::eval(vm, r);
+                    acc[0] += vm;
+                    // Fourier coefficients of the potential, rfft(Vm)[m] (nbls.py:194-201)
                     for (int m = 1; m <= nov; m++) {
-                        const double re = acc[2 * m - 1], im = acc[2 * m];
-                        acc[2 * m - 1] = hypot(re, im);
-                        acc[2 * m] = atan2(im, re);
+                        double sn, cs;
+                        sincospi((double)((2 * m * k) % (2 * SONIC_NPC)) * (1.0 / SONIC_NPC), &sn, &cs);
+                        acc[2 * m - 1] += vm * cs;
+                        acc[2 * m] -= vm * sn;
                     }
-                    // lane v holds table v
-                    double mine = 0.0;
 #pragma unroll
-                    for (int v = 0; v < NV; v++) {
-                        const int tv = v <= 2 * nov ? v : v - 2 * SONIC_MAX_OVERTONES + 2 * nov;   // table of slot v
-                        const bool used = v <= 2 * nov || v > 2 * SONIC_MAX_OVERTONES;
-                        if (used && lane == tv) mine = acc[v];
+                    for (int v = 0; v < NR; v++) acc[1 + 2 * MOV + v] += r[v];
+                }
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    double t = acc[v];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    acc[v] = t * (1.0 / (double)SONIC_NPC);
+                }
+                // amplitude-phase form of the overtone coefficients
+                for (int m = 1; m <= nov; m++) {
+                    const double re = acc[2 * m - 1], im = acc[2 * m];
+                    acc[2 * m - 1] = hypot(re, im);
+                    acc[2 * m] = atan2(im, re);
+                }
+                // every lane holds all sums: the lane of this entry keeps them
+                if (lane == fill) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) keep[v] = bad ? nan("") : acc[v];
+                }
+                fill++;
+                const bool last = (pt + 1 == p_last) && (j + 1 == nfs);
+                if (fill == 32 || last) {
+                    // one store per table: slot v of `keep` is table v (V, overtone pairs) or, past the
+                    // overtone slots, rate v - 2 (MOV - nov)
+                    if (lane < fill) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++) {
+                            const bool used = v <= 2 * nov || v > 2 * MOV;
+                            const int tv = v <= 2 * nov ? v : v - 2 * MOV + 2 * nov;
+                            if (used) a.out[(long long)tv * n * nfs + e_run + lane] = keep[v];
+                        }
                     }
-                    if (lane < nvar) res[lane * TILE + pl * nj + jj] = bad ? nan("") : mine;
+                    e_run += fill;
+                    fill = 0;
                 }
             }
-            __syncthreads();
-            // the tile of every table is one contiguous run when nj == nfs (else one run per point)
-            const int per_table = npt * nj;
-            for (int idx = threadIdx.x; idx < nvar * per_table; idx += 32 * SONIC_AVG_WARPS) {
-                const int v = idx / per_table, r = idx - v * per_table;
-                const int pl = r / nj, jj = r - pl * nj;
-                a.out[((long long)v * n + pt0 + pl) * nfs + j0 + jj] = res[v * TILE + r];
-            }
-            __syncthreads();
         }
     }
 }
@@ -855,24 +856,16 @@ static cudaError_t launch_average(SonicPlan* p, int k) {
     a.n = p->n_out_k[k];
     a.nfs = p->nfs; a.nov = p->nov;
     if (a.n == 0) return cudaSuccess;
-    // tile: up to 256 (point, fs) entries per table and block; several points per warp only when
-    // all coverage fractions fit one tile (the capacitance profile of a point is staged once)
-    if (p->nfs <= 32) {
-        a.j_tile = p->nfs;
-        int pt = 256 / p->nfs;
-        pt = pt < SONIC_AVG_WARPS ? SONIC_AVG_WARPS : (pt > 32 ? 32 : pt);
-        a.pt_tile = pt / SONIC_AVG_WARPS * SONIC_AVG_WARPS;
-    } else {
-        a.j_tile = p->nfs < 128 ? p->nfs : 128;
-        a.pt_tile = SONIC_AVG_WARPS;
+    // points per warp chunk: whole points, a multiple of 32 entries (full 256-byte runs)
+    {
+        int g = 32, m = p->nfs % 32;
+        while (m) { const int t = g % m; g = m; m = t; }      // gcd(32, nfs)
+        a.pts_per_chunk = 32 / g;
     }
-    const int nvar = 1 + 2 * p->nov + SonicRates<NID>::N;
-    const size_t smem = ((size_t)SONIC_AVG_WARPS * SONIC_NPC + (size_t)nvar * a.pt_tile * a.j_tile) * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(sonic_average_kernel<NID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    long long blocks = (a.n + a.pt_tile - 1) / a.pt_tile;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
-    sonic_average_kernel<NID><<<(int)blocks, 32 * SONIC_AVG_WARPS, smem, p->stream>>>(a);
+    long long blocks = ((a.n + a.pts_per_chunk - 1) / a.pts_per_chunk + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    if (p->nov) sonic_average_kernel<NID, true><<<(int)blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(a);
+    else sonic_average_kernel<NID, false><<<(int)blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(a);
     return cudaGetLastError();
 }
 
