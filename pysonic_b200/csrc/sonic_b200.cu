@@ -37,20 +37,35 @@
 #define SONIC_BLOCKS_PER_SM 2      /* 3 (168 registers, 72 B of spills) measured slower: 2.71 s vs 2.37 s on C2 */
 #endif
 #define SONIC_HIST_STRIDE SONIC_BLOCK   /* per-lane indexed storage interleaved across the block */
-/* tick time of a warp with k busy lanes relative to a lone lane: 1 + GAIN (1 - exp(-(k - 1) / KDEC)) (measured) */
 /* warps with at most this many busy lanes run the nested tick (0 = never) */
 #ifndef SONIC_LONE_MAXK
 #define SONIC_LONE_MAXK 1
 #endif
-/* SMs that keep one warp per scheduler for the longest chains (the other block of the SM is parked) */
-#ifndef SONIC_SCHED_EXCL_SMS
-#define SONIC_SCHED_EXCL_SMS 8
+/* 1 = a warp whose busy set is a single lane runs the nested tick on any SM (measured: C2 2.02 s instead of 1.37 s --
+   two instruction streams on one SM thrash its instruction cache); 0 = only in blocks the host marks (SMs that host
+   nothing but one-point warps) */
+#ifndef SONIC_LONE_DYNAMIC
+#define SONIC_LONE_DYNAMIC 0
 #endif
-#ifndef SONIC_SCHED_GAIN
-#define SONIC_SCHED_GAIN 1.8
+/* budgeted warps go to full width once their initial points are done (see the kernel) */
+#ifndef SONIC_WIDEN
+#define SONIC_WIDEN 1
 #endif
-#ifndef SONIC_SCHED_KDEC
-#define SONIC_SCHED_KDEC 4.0
+/* relative to the tick of a lone lane in the register-resident run with four such warps on its SM (1.21 us): the same with
+   eight warps on the SM (1.63 us), and a lone lane of a staged warp among other staged warps (2.0 us) */
+#ifndef SONIC_SCHED_LONE8_RATIO
+#define SONIC_SCHED_LONE8_RATIO 1.35
+#endif
+/* the points of the full-width queue are short: start-up (initial deflection read, first Adams steps of every cycle) and
+   partly empty warps make a lane-tick there cost more than in the calibration runs on long chains (5.5-7.5 us per
+   right-hand side measured on the bulk of C2 against 4.8 us) */
+/* budgeted warps share their SM with full-width warps and tick slower than in the calibration runs, where every warp of the
+   device holds the same number of lanes (scan over five workloads: profiles/README.md) */
+#ifndef SONIC_SCHED_STAGED_SLOWDOWN
+#define SONIC_SCHED_STAGED_SLOWDOWN 1.3
+#endif
+#ifndef SONIC_SCHED_QUEUE_OVERHEAD
+#define SONIC_SCHED_QUEUE_OVERHEAD 1.6
 #endif
 
 #include "../../include/sonic_b200.h"
@@ -113,6 +128,9 @@ struct SonicJob {
     long long n;
     int probe;                 // 1 = record the block placement and return
     const int* block_nested;   // [blocks]: 1 = this block runs the nested tick (plans whose warps hold one point at a time)
+    const int* block_group;    // [blocks]: SM group of a block whose SM hosts nothing but one-point warps, else -1
+    int* group_left;           // [groups]: warps of the group still on their initial chain
+    int widen;                 // 1 = budgeted warps go to full width once their initial points are done
 };
 
 __constant__ SonicTables c_tables;
@@ -191,7 +209,16 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
 #endif
     int cap = job.warp_cap[gwarp];
     long long q_init = (lane < cap) ? (long long)job.warp_first[gwarp] + lane : -1;
+    if (q_init >= job.n) q_init = -1;
     bool exhausted = false;
+    // A budgeted warp goes to full width once all of its initial points are done; on an SM that hosts nothing but
+    // one-point warps (group >= 0) only when every warp of the SM has got there -- until then it keeps taking single
+    // points from the queue, so that the SM runs one instruction stream at a time.
+    bool is_init = false;                  // this lane works on one of the warp's initial points
+    int init_left = __popc(__ballot_sync(0xffffffffu, q_init >= 0));
+    const int group = job.block_group ? job.block_group[blockIdx.x] : -1;
+    bool released = init_left == 0;        // nothing (left) to wait for
+    if (released && group >= 0 && cap > 0 && cap < 32 && lane == 0) atomicSub(&job.group_left[group], 1);
     if (cap == 0) {
         // Parked warp: it shares its SM with the very longest chains of the grid, which then have a
         // scheduler (and the SM's instruction cache) almost to themselves.  It stays out of the way
@@ -203,14 +230,24 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     }
 
     while (true) {
+        if (released && cap < 32 && job.widen) {
+            int left = 0;
+            if (group >= 0) {
+                if (lane == 0) left = *reinterpret_cast<volatile int*>(job.group_left + group);
+                left = __shfl_sync(0xffffffffu, left, 0);
+            }
+            if (left <= 0) cap = 32;
+        }
         if (pt < 0 && !exhausted && lane < cap) {
             // (re)fill this lane: its initial point first, then the shared work queue
             unsigned long long q;
             if (q_init >= 0) {
                 q = (unsigned long long)q_init;
                 q_init = -1;
+                is_init = true;
             } else {
                 q = atomicAdd(job.counter, 1ULL);
+                is_init = false;
             }
             if (q < (unsigned long long)job.n) {
                 pt = job.order[q];
@@ -249,15 +286,13 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
         // tick until a lane of this warp finishes its point (the set of busy lanes is fixed till then)
         bool fin = false;
 #if SONIC_LONE_MAXK > 0
-        if (nested) {
-            // few busy lanes (the long chains the host hands out to sparsely populated warps): nothing to
-            // share between lanes, each follows its own path through the nested tick
+        if ((nested || SONIC_LONE_DYNAMIC) && __popc(wmask) == 1) {
+            // a lane alone in its warp (the long chains the host hands out one per warp, on SMs that host
+            // nothing else): nothing to share with other lanes, it follows its own path -- register-resident
+            // runs at fixed order, generic nested ticks in between
             do {
                 if (active) {
-                    double fv[3];
-                    if (OVT) sonic_update_charge(p, s.tn);
-                    if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;
-                    sonic_tick_lone(s, H, &tab, p, sink, period, fv);
+                    sonic_lone_advance<OVT>(s, H, &tab, p, sink, period);
                     fin = s.phase == PH_DONE;
                 }
             } while (!__any_sync(0xffffffffu, fin));
@@ -281,6 +316,14 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
             job.tpoint[pt] = (double)(sonic_globaltimer() - t_start) * 1e-9;
             pt = -1;
         }
+        if (!released) {
+            init_left -= __popc(__ballot_sync(0xffffffffu, fin && is_init));
+            if (init_left <= 0) {
+                released = true;
+                if (group >= 0 && lane == 0) atomicSub(&job.group_left[group], 1);
+            }
+        }
+        if (fin) is_init = false;
     }
 }
 
@@ -818,6 +861,8 @@ struct SonicPlan {
     int *d_order = nullptr, *d_ia = nullptr, *d_ia_out = nullptr, *d_umap = nullptr, *d_sel = nullptr;
     int *d_warp_first = nullptr, *d_warp_cap = nullptr, *d_block_smid = nullptr, *d_ncycles = nullptr;
     int* d_block_nested = nullptr;
+    int *d_block_group = nullptr, *d_group_left0 = nullptr, *d_group_left = nullptr;
+    int n_groups = 0;
     double *d_f = nullptr, *d_A = nullptr, *d_Q = nullptr, *d_fs = nullptr, *d_ov = nullptr, *d_Qout = nullptr;
     double *d_z0 = nullptr, *d_zbuf = nullptr, *d_ngbuf = nullptr, *d_tpoint = nullptr, *d_out = nullptr;
     unsigned *d_status = nullptr, *d_nfe = nullptr, *d_nje = nullptr, *d_nsteps = nullptr;
@@ -1082,10 +1127,12 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
     const size_t o_counter0 = take(sizeof(unsigned long long));
     const size_t o_wfirst = take(nwarps * sizeof(int)), o_wcap = take(nwarps * sizeof(int));
     const size_t o_nested = take(blocks * sizeof(int));
+    const size_t o_bgroup = take(blocks * sizeof(int)), o_group0 = take(blocks * sizeof(int));
     const size_t in_bytes = (off + 255) & ~(size_t)255;
     off = in_bytes;
     const size_t o_z0 = take(n * sizeof(double)), o_nje = take(n * sizeof(unsigned)), o_nsteps = take(n * sizeof(unsigned));
     const size_t o_counter = take(sizeof(unsigned long long)), o_smid = take(blocks * sizeof(int));
+    const size_t o_group = take(blocks * sizeof(int));
     const size_t o_result = take(0);
     const size_t r0 = off;
     const size_t o_out = take(p->out_count * sizeof(double)), o_ncyc = take(n * sizeof(int)), o_status = take(n * sizeof(unsigned));
@@ -1111,6 +1158,8 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
     p->d_umap = (int*)(D + o_umap); p->d_sel = (int*)(D + o_sel);
     p->d_warp_first = (int*)(D + o_wfirst); p->d_warp_cap = (int*)(D + o_wcap);
     p->d_block_nested = (int*)(D + o_nested);
+    p->d_block_group = (int*)(D + o_bgroup); p->d_group_left0 = (int*)(D + o_group0); p->d_group_left = (int*)(D + o_group);
+    p->n_groups = (int)blocks;
     p->d_z0 = (double*)(D + o_z0); p->d_nje = (unsigned*)(D + o_nje); p->d_nsteps = (unsigned*)(D + o_nsteps);
     p->d_counter0 = (unsigned long long*)(D + o_counter0);
     p->d_counter = (unsigned long long*)(D + o_counter); p->d_block_smid = (int*)(D + o_smid);
@@ -1181,12 +1230,10 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
 
     // ---- lane budgets (see the kernel).  Warps are walked SM by SM (all warps of all blocks of one
     // SM, then the next SM), each taking the next `cap` points of the sorted list, so that the
-    // most expensive points end up alone in their warp on SMs that host nothing but such warps:
-    // a lone lane ticks in t1 there, but slower next to full, phase-diverged warps
-    // (instruction-cache and issue contention), and a warp with k busy lanes in about
-    //   t(k) = t1 (1 + GAIN (1 - exp(-(k - 1) / KDEC))),   t(32) = (1 + GAIN) t1.
-    // Every chain c should finish within the deadline T, so a warp whose most expensive
-    // point has predicted chain length c may run at t <= (T / c) t1.
+    // most expensive points end up alone in their warp on SMs that host nothing but such warps.
+    // A warp with k busy lanes ticks in t(k) (measured table below, 1.9 us for k = 1 to 4.8 us
+    // for k = 32); every chain c should finish within the deadline T, so a warp whose most
+    // expensive point has predicted chain length c may keep k lanes busy with c t(k) <= T.
     int* wfirst = (int*)(H + o_wfirst);
     int* wcap = (int*)(H + o_wcap);
     for (int w = 0; w < nwarps; w++) { wfirst[w] = (int)n; wcap[w] = (int)lpw; }
@@ -1194,48 +1241,92 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         std::vector<int> border(blocks);
         for (int b = 0; b < (int)blocks; b++) border[b] = b;
         std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return smid[x] < smid[y]; });
-        double GAIN = SONIC_SCHED_GAIN, KDEC = SONIC_SCHED_KDEC;
-        if (const char* e = getenv("SONIC_SCHED_GAIN")) GAIN = atof(e);      // (tuning runs)
-        if (const char* e = getenv("SONIC_SCHED_KDEC")) KDEC = atof(e);
-        const double T32 = 1.0 + GAIN;                                       // t(32) / t1
+        // Tick times, measured (tools/gpu_tk.py, tools/gpu_lone_rates.py: every warp of the device with k busy lanes on
+        // chains of the same kind), in units of t_f = 1.21 us, the tick of a lone lane in the register-resident run on an
+        // SM that hosts four such warps, one per scheduler: R8 = the same with eight warps on the SM (1.63 us), tk[k] = a
+        // staged warp with k busy lanes (1.89 us for k = 1, 2.57, 3.01, 3.33, ... 4.80 us for k = 32).
+        static const double tk_us[33] = {0, 1.885, 2.568, 3.013, 3.334, 3.56, 3.760, 3.91, 4.047, 4.13, 4.21, 4.28, 4.338,
+                                         4.38, 4.42, 4.46, 4.499, 4.53, 4.56, 4.59, 4.61, 4.64, 4.66, 4.69, 4.713, 4.73, 4.74,
+                                         4.75, 4.77, 4.78, 4.79, 4.80, 4.805};
+        double R8 = SONIC_SCHED_LONE8_RATIO, SLOW = SONIC_SCHED_STAGED_SLOWDOWN;
+        if (const char* e = getenv("SONIC_SCHED_LONE8_RATIO")) R8 = atof(e);    // (tuning runs)
+        if (const char* e = getenv("SONIC_SCHED_STAGED_SLOWDOWN")) SLOW = atof(e);
+        double tk[33];
+        for (int k = 1; k <= 32; k++) tk[k] = tk_us[k] / 1.21 * SLOW;
+        double QOV = SONIC_SCHED_QUEUE_OVERHEAD;
+        if (const char* e = getenv("SONIC_SCHED_QUEUE_OVERHEAD")) QOV = atof(e);
+        const double RS = tk[1], T32 = tk[32] * QOV;
         std::vector<double> chain(n), tail(n + 1, 0.0);               // predicted ticks, suffix sums
         for (long long i = 0; i < n; i++) chain[i] = exp(cost[order[i]]);
         for (long long i = n - 1; i >= 0; i--) tail[i] = tail[i + 1] + chain[i];
-        // lanes a warp may keep busy if its longest chain c has to finish within T (units of t1)
+        // lanes a staged warp may keep busy if its longest chain c has to finish within T
         auto cap_for = [&](double c, double T) {
-            const double x = (T / c - 1.0) / GAIN;
-            if (x >= 0.98) return 32;
-            if (x <= 0.0) return 1;
-            const int k = (int)(1.0 - KDEC * log(1.0 - x));
-            return k < 1 ? 1 : (k > 32 ? 32 : k);
+            int k = 1;
+            while (k < 32 && c * tk[k + 1] <= T) k++;
+            return k;
         };
-        // Pick the deadline T: the budgeted warps finish by T by construction; whatever is not
-        // handed out statically runs on the remaining warps at full width.  A small T isolates
-        // the long chains but leaves few full-width warps; scan T upwards from the longest chain
-        // and keep the T with the smallest predicted makespan max(T, queue time).
-        double best_T = chain[0], best_span = 1e300;
-        for (double T = chain[0] * 1.02; T < chain[0] * 40.0; T *= 1.04) {
-            long long pos = 0;
+        // One decision, the deadline T.  It fixes everything else: chains too long for eight lone warps per SM
+        // (c R8 > T) go to tier-1 SMs, which keep one warp per scheduler for them and park their second block;
+        // chains too long for a lone lane of a staged warp (c RS > T) go to tier-2 SMs, eight per SM; both kinds of
+        // SM host nothing but one-point warps in the register-resident run (one instruction stream in the SM's
+        // cache).  The other SMs run staged warps: budgets while the longer chains last, full width on the queue
+        // afterwards -- as do the lone warps once their chain is done.  Keep the T with the smallest predicted makespan.
+        const bool can_excl = lpw > 1;
+        const int wps = warps_per_block * 2;                                     // warps of one SM
+        int force1 = -1, force2 = -1, force_cap = 0;
+        if (const char* e = getenv("SONIC_SCHED_FORCE_CAP")) force_cap = atoi(e);
+        if (const char* e = getenv("SONIC_SCHED_TIER1_SMS")) force1 = atoi(e);
+        if (const char* e = getenv("SONIC_SCHED_TIER2_SMS")) force2 = atoi(e);
+        auto count_above = [&](double c) {                                      // chains longer than c (sorted descending)
+            return (long long)(std::lower_bound(chain.begin(), chain.end(), c, [](double a, double b) { return a > b; }) - chain.begin());
+        };
+        double best_T = chain[0] * RS, best_span = 1e300;
+        int best_E1 = 0, best_E2 = 0;
+        for (double T = chain[0] * 1.02; T < chain[0] * 60.0; T *= 1.03) {
+            int E1 = 0, E2 = 0;
+            if (can_excl) {
+                const long long n1 = count_above(T / R8), n12 = count_above(T / RS);
+                E1 = (int)((n1 + wps / 2 - 1) / (wps / 2));
+                if (force1 >= 0) E1 = force1;
+                const long long in1 = std::min<long long>((long long)E1 * (wps / 2), n);
+                E2 = (int)((std::max(n12 - in1, 0LL) + wps - 1) / wps);
+                if (force2 >= 0) E2 = force2;
+                if ((E1 + E2) * wps > nwarps * 3 / 4) continue;                  // (a later deadline needs fewer)
+            }
+            const long long nl1 = std::min<long long>((long long)E1 * (wps / 2), n);
+            const long long nl = std::min<long long>(nl1 + (long long)E2 * wps, n);
+            if ((nl1 > 0 && chain[0] > T) || (nl > nl1 && chain[nl1] * R8 > T)) continue;
+            const int staged_warps = nwarps - (E1 + E2) * wps;
+            long long pos = nl;
             int used = 0;
-            while (used < nwarps && pos < n) {
+            double have = 0.0;               // warp-time left for the full-width queue before T
+            while (used < staged_warps && pos < n) {
                 const int k = cap_for(chain[pos], T);
                 if (k >= (int)lpw) break;
+                // (a budgeted warp goes to full width when its own chains are done)
+                have += std::max(0.0, T - chain[pos] * tk[k]);
                 pos += k;
                 used++;
             }
-            const int full = nwarps - used;
-            const double queue = full > 0 ? tail[pos] / (32.0 * full) * T32 : (pos < n ? 1e300 : 0.0);
+            // warp-time the full-width queue needs, and what the warps can deliver by T
+            const double need = tail[pos] * T32 / 32.0;
+            have += (double)(staged_warps - used) * T;
+            // (the lone warps of an SM go to full width together, when the SM's longest chain is done)
+            for (long long i = 0; i < nl1; i += wps / 2) have += (wps / 2) * std::max(0.0, T - chain[i]);
+            for (long long i = nl1; i < nl; i += wps) have += wps * std::max(0.0, T - chain[i] * R8);
+            const double queue = have > 0.0 ? T * need / have : (pos < n ? 1e300 : 0.0);
             const double span = T > queue ? T : queue;
-            if (span < best_span) { best_span = span; best_T = T; }
+            if (span < best_span) { best_span = span; best_T = T; best_E1 = E1; best_E2 = E2; }
             if (queue <= T) break;        // larger T only makes the deadline later
         }
-        // The first `excl` SMs of the walk keep one warp per scheduler for the longest chains and
-        // park the others (blocks alternate on an SM; the probe tells which blocks share it).
-        int excl = SONIC_SCHED_EXCL_SMS;
-        if (const char* e = getenv("SONIC_SCHED_EXCL_SMS")) excl = atoi(e);
-        if (lpw <= 1 || blocks < 2 * (long long)dev.sm_count) excl = 0;     // only when the device is full
+        if (getenv("SONIC_DEBUG"))
+            fprintf(stderr, "[sonic] schedule: %d + %d SMs of lone warps, deadline %.3g ticks (longest chain %.3g), predicted span %.3g\n",
+                    best_E1, best_E2, best_T, chain[0], best_span);
         long long pos = 0;
         std::vector<int> excl_block(blocks, 0);
+        int* bgroup = (int*)(H + o_bgroup);
+        int* group0 = (int*)(H + o_group0);
+        for (int b = 0; b < (int)blocks; b++) { bgroup[b] = -1; group0[b] = 0; }
         int sm_rank = -1, last_sm = -1, blk_on_sm = 0;
         for (int r = 0; r < nwarps; r++) {
             const int b = border[r / warps_per_block];
@@ -1244,14 +1335,17 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
                 if (smid[b] != last_sm) { last_sm = smid[b]; sm_rank++; blk_on_sm = 0; }
                 else blk_on_sm++;
             }
-            if (sm_rank < excl) excl_block[b] = 1;
-            if (sm_rank < excl && blk_on_sm >= 1) {
+            const bool lone_sm = sm_rank < best_E1 + best_E2;
+            if (lone_sm) { excl_block[b] = 1; bgroup[b] = sm_rank; }
+            if (sm_rank < best_E1 && blk_on_sm >= 1) {
                 wfirst[gw] = (int)n;
                 wcap[gw] = 0;                  // parked
                 continue;
             }
-            if (pos >= n) continue;
-            int cap = cap_for(chain[pos], best_T);
+            if (lone_sm) group0[sm_rank]++;    // every working warp of the group reports once
+            if (pos >= n) { if (lone_sm) wcap[gw] = 1; continue; }
+            int cap = lone_sm ? 1 : cap_for(chain[pos], best_T);
+            if (force_cap > 0) cap = force_cap;                                  // (calibration runs)
             if (cap > (int)lpw) cap = (int)lpw;
             wfirst[gw] = (int)pos;
             wcap[gw] = cap;
@@ -1263,7 +1357,7 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         // single points: C1 -12 %).  On a grid that mixes sparse and full warps it is a loss even on SMs
         // that host nothing but one-point warps (C2: 1.36 s instead of 1.26 s, profiles/README.md).
         int* nested = (int*)(H + o_nested);
-        int mode = lpw == 1 ? 1 : 0;
+        int mode = lpw == 1 ? 1 : 2;
         if (const char* e = getenv("SONIC_NESTED")) mode = atoi(e);      // (experiments)
         for (int b = 0; b < (int)blocks; b++) nested[b] = (mode == 2) ? excl_block[b] : mode;
     }
@@ -1404,9 +1498,13 @@ int sonic_plan_launch(SonicPlan* p) {
     job.warp_first = p->d_warp_first; job.warp_cap = p->d_warp_cap;
     job.block_smid = p->d_block_smid; job.probe = 0;
     job.block_nested = p->d_block_nested;
+    job.block_group = p->d_block_group; job.group_left = p->d_group_left;
+    job.widen = SONIC_WIDEN;
+    if (const char* e = getenv("SONIC_WIDEN")) job.widen = atoi(e);      // (tuning runs)
     cudaEvent_t* ev = p->ws->ev;
     p->result_on_host = false;
     CUDA_TRY(cudaMemcpyAsync(p->d_counter, p->d_counter0, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_group_left, p->d_group_left0, p->n_groups * sizeof(int), cudaMemcpyDeviceToDevice, p->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_stats, 0, 8 * sizeof(unsigned long long), p->stream));
     CUDA_TRY(cudaEventRecord(ev[0], p->stream));
     sonic_z0_kernel<<<(unsigned)((p->n + 127) / 128), 128, 0, p->stream>>>(job);

@@ -659,11 +659,48 @@ enum SonicPhase : int {
 #define SONIC_H_SIZE 54
 
 struct SonicHist {
+    static constexpr bool REG = false;
     double* base;
     SONIC_HDM double& at(int k) const { return base[k * SONIC_HIST_STRIDE]; }
     SONIC_HDM double& yh(int j, int i) const { return base[(3 * j + i) * SONIC_HIST_STRIDE]; }
     SONIC_HDM double& wm(int k) const { return base[(SONIC_H_WM + k) * SONIC_HIST_STRIDE]; }
+    SONIC_HDM const SonicHist& store() const { return *this; }
 };
+
+// The same history while a lane advances in the BDF family (orders 1-5) in the register-resident run
+// (sonic_bdf_run): the Nordsieck columns 0..5 (column 5 = lmax - 1 is also where the corrector sum is
+// parked for the order-increase test) are plain variables.  Every access has a compile-time index:
+// loops over the order are predicated (`if (j <= nq)`) or dispatched on the order to unrolled blocks
+// (sonic_pascal_cols, sonic_interp_cols).  The iteration matrix and the convergence accumulators stay
+// in the indexed storage `S`.  The pieces of the tick are templates over the history type, so both
+// forms perform the same operations in the same order.
+struct SonicRegHist {
+    static constexpr bool REG = true;
+    double c[6][3];
+    SonicHist S;
+    SONIC_HDM double& at(int k) const { return S.at(k); }
+    SONIC_HDM double& yh(int j, int i) { return c[j][i]; }
+    SONIC_HDM double& wm(int k) const { return S.wm(k); }
+    SONIC_HDM const SonicHist& store() const { return S; }
+    SONIC_HDM void load() {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            c[j][0] = S.yh(j, 0); c[j][1] = S.yh(j, 1); c[j][2] = S.yh(j, 2);
+        }
+    }
+    SONIC_HDM void spill() const {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            S.yh(j, 0) = c[j][0]; S.yh(j, 1) = c[j][1]; S.yh(j, 2) = c[j][2];
+        }
+    }
+};
+
+#if defined(__CUDA_ARCH__)
+#define SONIC_ASSUME(x) __builtin_assume(x)
+#else
+#define SONIC_ASSUME(x) do { if (!(x)) __builtin_unreachable(); } while (0)
+#endif
 
 struct SonicLane {
     // ---- integrator ----
@@ -702,11 +739,22 @@ SONIC_HD double sonic_mnorm(const double v[3], const double w[3]) {
     return sonic_mnorm3(v[0], v[1], v[2], w);
 }
 
-SONIC_HD double sonic_mnorm_col(const SonicHist& H, int j, const double w[3]) {
-    return sonic_mnorm3(H.yh(j, 0), H.yh(j, 1), H.yh(j, 2), w);
+template <class HT>
+SONIC_HD double sonic_mnorm_col(HT& H, int j, const double w[3]) {
+    if constexpr (HT::REG) {
+        // column j = 1..5 picked with selects (compile-time indices only)
+        double v0 = H.yh(1, 0), v1 = H.yh(1, 1), v2 = H.yh(1, 2);
+#pragma unroll
+        for (int k = 2; k <= 5; k++)
+            if (j == k) { v0 = H.yh(k, 0); v1 = H.yh(k, 1); v2 = H.yh(k, 2); }
+        return sonic_mnorm3(v0, v1, v2, w);
+    } else {
+        return sonic_mnorm3(H.yh(j, 0), H.yh(j, 1), H.yh(j, 2), w);
+    }
 }
 
-SONIC_HD void sonic_ewset(SonicLane& s, const SonicHist& H) {
+template <class HT>
+SONIC_HD void sonic_ewset(SonicLane& s, HT& H) {
     s.ewt[0] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 0)) + SONIC_ATOL);
     s.ewt[1] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 1)) + SONIC_ATOL);
     s.ewt[2] = sonic_rcp(SONIC_RTOL * fabs(H.yh(0, 2)) + SONIC_ATOL);
@@ -729,7 +777,31 @@ SONIC_HD void sonic_set_order(SonicLane& s, const SonicTables* T) {
 
 // Multiply yh by the Pascal triangle (prediction) or its inverse (retraction).
 // For jb = 1..nq the sweep updates columns nq-jb .. nq-1 (0-based) in ascending order.
-SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double sign) {
+// the sweeps of the Pascal-triangle product for order K, unrolled on named columns
+template <int K, class HT>
+SONIC_HD void sonic_pascal_cols(HT& H, const double sign) {
+#pragma unroll
+    for (int jb = 1; jb <= K; jb++) {
+#pragma unroll
+        for (int j = K - jb; j < K; j++) {
+            H.yh(j, 0) += sign * H.yh(j + 1, 0);
+            H.yh(j, 1) += sign * H.yh(j + 1, 1);
+            H.yh(j, 2) += sign * H.yh(j + 1, 2);
+        }
+    }
+}
+
+template <class HT>
+SONIC_HD void sonic_pascal(const SonicLane& s, HT& H, const double sign) {
+    if constexpr (HT::REG) {
+        switch (s.nq) {
+            case 1: sonic_pascal_cols<1>(H, sign); break;
+            case 2: sonic_pascal_cols<2>(H, sign); break;
+            case 3: sonic_pascal_cols<3>(H, sign); break;
+            case 4: sonic_pascal_cols<4>(H, sign); break;
+            default: sonic_pascal_cols<5>(H, sign); break;
+        }
+    } else {
     const int nq = s.nq;
     if (sign > 0.0 && nq <= 5) {
         // Low orders (every BDF order): columns held in registers, top-aligned
@@ -776,6 +848,7 @@ SONIC_HD void sonic_pascal(const SonicLane& s, const SonicHist& H, const double 
             H.yh(j, 2) += sign * H.yh(j + 1, 2);
         }
     }
+    }
 }
 
 // A pending step-size change: every place of the tick that decides one files it here and the
@@ -787,13 +860,15 @@ struct SonicRescaleReq {
 };
 
 // Apply a step-size ratio: bound it, restrict by the Adams stability region, rescale history.
-SONIC_HD void sonic_rescale(SonicLane& s, const SonicHist& H, const SonicTables* T, double rh) {
+template <class HT>
+SONIC_HD void sonic_rescale(SonicLane& s, HT& H, const SonicTables* T, double rh) {
+    const int nq = s.nq;
     rh = fmin(rh, s.rmax);
     if (s.meth == 1) {
         s.irflag = 0;
         const double pdh = fmax(fabs(s.h) * s.pdlast, 0.000001);
-        if (rh * pdh * 1.00001 >= T->sm1[s.nq - 1]) {
-            rh = sonic_div(T->sm1[s.nq - 1], pdh);
+        if (rh * pdh * 1.00001 >= T->sm1[nq - 1]) {
+            rh = sonic_div(T->sm1[nq - 1], pdh);
             s.irflag = 1;
         }
     }
@@ -802,26 +877,29 @@ SONIC_HD void sonic_rescale(SonicLane& s, const SonicHist& H, const SonicTables*
 #pragma unroll
     for (int j = 1; j <= 5; j++) {
         r *= rh;
-        if (j <= s.nq) {
+        if (j <= nq) {
             H.yh(j, 0) *= r;
             H.yh(j, 1) *= r;
             H.yh(j, 2) *= r;
         }
     }
+    if constexpr (!HT::REG) {
 #pragma unroll 1
-    for (int j = 6; j <= s.nq; j++) {
-        r *= rh;
-        H.yh(j, 0) *= r;
-        H.yh(j, 1) *= r;
-        H.yh(j, 2) *= r;
+        for (int j = 6; j <= nq; j++) {
+            r *= rh;
+            H.yh(j, 0) *= r;
+            H.yh(j, 1) *= r;
+            H.yh(j, 2) *= r;
+        }
     }
     s.h *= rh;
     s.rc *= rh;
-    s.ialth = s.nq + 1;
+    s.ialth = nq + 1;
 }
 
 // Prediction: advance tn, apply Pascal triangle, set the evaluation point.
-SONIC_HD void sonic_predict(SonicLane& s, const SonicHist& H) {
+template <class HT>
+SONIC_HD void sonic_predict(SonicLane& s, HT& H) {
     if (fabs(s.rc - 1.0) > 0.3) s.ipup = s.miter;
     if (s.nst >= s.nslp + 20) s.ipup = s.miter;
     s.tn += s.h;
@@ -929,33 +1007,57 @@ SONIC_HD void sonic_lusolve3(const SonicHist& H, int ipvt_packed, double b[3]) {
 }
 
 // Interpolate the solution at time t from the Nordsieck history (k = 0 derivative).
-SONIC_HD void sonic_interp(const SonicLane& s, const SonicHist& H, double t, double out[3]) {
+// Horner evaluation from column K down, on named columns
+template <int K, class HT>
+SONIC_HD void sonic_interp_cols(HT& H, const double sfrac, double out[3]) {
+    double o0 = H.yh(K, 0), o1 = H.yh(K, 1), o2 = H.yh(K, 2);
+#pragma unroll
+    for (int j = K - 1; j >= 0; j--) {
+        o0 = H.yh(j, 0) + sfrac * o0;
+        o1 = H.yh(j, 1) + sfrac * o1;
+        o2 = H.yh(j, 2) + sfrac * o2;
+    }
+    out[0] = o0; out[1] = o1; out[2] = o2;
+}
+
+template <class HT>
+SONIC_HD void sonic_interp(const SonicLane& s, HT& H, double t, double out[3]) {
     const double sfrac = sonic_div(t - s.tn, s.h);
     const int nq = s.nq;
-    if (nq <= 5) {
-        // Horner from the top column down; columns above nq are skipped (compile-time addresses)
-        double o0 = 0.0, o1 = 0.0, o2 = 0.0;
-#pragma unroll
-        for (int j = 5; j >= 0; j--) {
-            if (j == nq) {
-                o0 = H.yh(j, 0); o1 = H.yh(j, 1); o2 = H.yh(j, 2);
-            } else if (j < nq) {
-                o0 = H.yh(j, 0) + sfrac * o0;
-                o1 = H.yh(j, 1) + sfrac * o1;
-                o2 = H.yh(j, 2) + sfrac * o2;
-            }
+    if constexpr (HT::REG) {
+        switch (nq) {
+            case 1: sonic_interp_cols<1>(H, sfrac, out); break;
+            case 2: sonic_interp_cols<2>(H, sfrac, out); break;
+            case 3: sonic_interp_cols<3>(H, sfrac, out); break;
+            case 4: sonic_interp_cols<4>(H, sfrac, out); break;
+            default: sonic_interp_cols<5>(H, sfrac, out); break;
         }
-        out[0] = o0; out[1] = o1; out[2] = o2;
-        return;
-    }
-    out[0] = H.yh(s.nq, 0);
-    out[1] = H.yh(s.nq, 1);
-    out[2] = H.yh(s.nq, 2);
+    } else {
+        if (nq <= 5) {
+            // Horner from the top column down; columns above nq are skipped (compile-time addresses)
+            double o0 = 0.0, o1 = 0.0, o2 = 0.0;
+#pragma unroll
+            for (int j = 5; j >= 0; j--) {
+                if (j == nq) {
+                    o0 = H.yh(j, 0); o1 = H.yh(j, 1); o2 = H.yh(j, 2);
+                } else if (j < nq) {
+                    o0 = H.yh(j, 0) + sfrac * o0;
+                    o1 = H.yh(j, 1) + sfrac * o1;
+                    o2 = H.yh(j, 2) + sfrac * o2;
+                }
+            }
+            out[0] = o0; out[1] = o1; out[2] = o2;
+            return;
+        }
+        out[0] = H.yh(s.nq, 0);
+        out[1] = H.yh(s.nq, 1);
+        out[2] = H.yh(s.nq, 2);
 #pragma unroll 1
-    for (int j = s.nq - 1; j >= 0; j--) {
-        out[0] = H.yh(j, 0) + sfrac * out[0];
-        out[1] = H.yh(j, 1) + sfrac * out[1];
-        out[2] = H.yh(j, 2) + sfrac * out[2];
+        for (int j = s.nq - 1; j >= 0; j--) {
+            out[0] = H.yh(j, 0) + sfrac * out[0];
+            out[1] = H.yh(j, 1) + sfrac * out[1];
+            out[2] = H.yh(j, 2) + sfrac * out[2];
+        }
     }
 }
 
@@ -1021,14 +1123,15 @@ SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepC
 
 // Choose the next order/step after a success (ialth == 0, iredo = 0) or an error-test failure
 // (iredo = 2).  Returns true if the step must be redone (predict again).  Sets the step size: exact powers.
-SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* T, double rhup,
+template <class HT>
+SONIC_HD bool sonic_select(SonicLane& s, HT& H, const SonicTables* T, double rhup,
                            int iredo, SonicStepCtx* ctx, SonicRescaleReq& rq) {
     const int l = s.nq + 1;
-    const int lmax = SONIC_LMAX(s);
+    const int lmax = HT::REG ? SONIC_MXORDS + 1 : SONIC_LMAX(s);
     double rhsm = sonic_rhsm0(s, T, ctx, true);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = SONIC_QUOT(sonic_mnorm_col(H, s.nq, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
+        const double ddn = SONIC_QUOT(sonic_mnorm_col(H, l - 1, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
         const double exdn = T->rk[s.nq];
         rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn, s.nq) + 0.0000013);
     }
@@ -1060,9 +1163,16 @@ SONIC_HD bool sonic_select(SonicLane& s, const SonicHist& H, const SonicTables* 
             return false;
         }
         const double r = SONIC_QUOT(SONIC_EL(s, T, l - 1), (double)l, T->rk[l]);
-        H.yh(l, 0) = s.acor[0] * r;
-        H.yh(l, 1) = s.acor[1] * r;
-        H.yh(l, 2) = s.acor[2] * r;
+        if constexpr (HT::REG) {
+            // (l = 2..5 here: l < lmax)
+#pragma unroll
+            for (int k = 2; k <= 5; k++)
+                if (l == k) { H.yh(k, 0) = s.acor[0] * r; H.yh(k, 1) = s.acor[1] * r; H.yh(k, 2) = s.acor[2] * r; }
+        } else {
+            H.yh(l, 0) = s.acor[0] * r;
+            H.yh(l, 1) = s.acor[1] * r;
+            H.yh(l, 2) = s.acor[2] * r;
+        }
         s.nq = l;
         sonic_set_order(s, T);
         rq.pending = true; rq.rh = rh; rq.rmax10 = (iredo == 0);
@@ -1275,7 +1385,8 @@ SONIC_HD void sonic_reset_order(SonicLane& s, const SonicHist& H, const SonicTab
 
 // Corrector update with savf (functional iteration or chord / Newton) and convergence test.
 // Outcome: converged, failed (corr_failed), or one more iterate (phase = PH_CORR_ITER).
-SONIC_HD void sonic_corrector(SonicLane& s, const SonicHist& H, const SonicTables* T, bool& converged,
+template <class HT>
+SONIC_HD void sonic_corrector(SonicLane& s, HT& H, const SonicTables* T, bool& converged,
                               bool& corr_failed) {
     const double el1 = SONIC_EL(s, T, 0);
     const double yh00 = H.yh(0, 0), yh01 = H.yh(0, 1), yh02 = H.yh(0, 2);
@@ -1295,7 +1406,7 @@ SONIC_HD void sonic_corrector(SonicLane& s, const SonicHist& H, const SonicTable
         d[0] = s.h * s.savf[0] - (yh10 + s.acor[0]);
         d[1] = s.h * s.savf[1] - (yh11 + s.acor[1]);
         d[2] = s.h * s.savf[2] - (yh12 + s.acor[2]);
-        sonic_lusolve3(H, s.ipvt, d);
+        sonic_lusolve3(H.store(), s.ipvt, d);
         s.del = sonic_mnorm(d, s.ewt);
         s.acor[0] += d[0]; s.acor[1] += d[1]; s.acor[2] += d[2];
         s.y[0] = yh00 + el1 * s.acor[0];
@@ -1341,7 +1452,8 @@ SONIC_HD bool sonic_error_test(SonicLane& s, const SonicTables* T) {
 }
 
 // Corrector failure without a current Jacobian: same step again with a fresh one.
-SONIC_HD void sonic_retry_with_jacobian(SonicLane& s, const SonicHist& H) {
+template <class HT>
+SONIC_HD void sonic_retry_with_jacobian(SonicLane& s, HT& H) {
     s.ipup = s.miter;
     s.m = 0;
     s.rate = 0.0;
@@ -1388,7 +1500,9 @@ SONIC_HD void sonic_retract(SonicLane& s, const SonicHist& H, bool cf, bool& do_
 }
 
 // The step is accepted: update the history.  Returns true when a method switch has to be considered.
-SONIC_HD bool sonic_accept(SonicLane& s, const SonicHist& H, const SonicTables* T) {
+template <class HT>
+SONIC_HD bool sonic_accept(SonicLane& s, HT& H, const SonicTables* T) {
+    const int nq = s.nq;
     s.kflag = 0;
     s.nst++;
     s.nsteps++;
@@ -1401,19 +1515,21 @@ SONIC_HD bool sonic_accept(SonicLane& s, const SonicHist& H, const SonicTables* 
         const double* el = &SONIC_EL(s, T, 0);
 #pragma unroll
         for (int j = 0; j <= 5; j++) {
-            if (j <= s.nq) {
+            if (j <= nq) {
                 const double e = el[j];
                 H.yh(j, 0) += e * s.acor[0];
                 H.yh(j, 1) += e * s.acor[1];
                 H.yh(j, 2) += e * s.acor[2];
             }
         }
+        if constexpr (!HT::REG) {
 #pragma unroll 1
-        for (int j = 6; j <= s.nq; j++) {
-            const double e = el[j];
-            H.yh(j, 0) += e * s.acor[0];
-            H.yh(j, 1) += e * s.acor[1];
-            H.yh(j, 2) += e * s.acor[2];
+            for (int j = 6; j <= nq; j++) {
+                const double e = el[j];
+                H.yh(j, 0) += e * s.acor[0];
+                H.yh(j, 1) += e * s.acor[1];
+                H.yh(j, 2) += e * s.acor[2];
+            }
         }
     }
     s.icount--;
@@ -1422,10 +1538,11 @@ SONIC_HD bool sonic_accept(SonicLane& s, const SonicHist& H, const SonicTables* 
 
 // Step/order bookkeeping after a success without method switch: every ialth steps prepare the
 // order/step selection (sel_mode = 1, candidate for an order increase in sel_rhup).
-SONIC_HD void sonic_after_accept(SonicLane& s, const SonicHist& H, const SonicTables* T, int& sel_mode,
+template <class HT>
+SONIC_HD void sonic_after_accept(SonicLane& s, HT& H, const SonicTables* T, int& sel_mode,
                                  double& sel_rhup) {
     const int l = s.nq + 1;
-    const int lmax = SONIC_LMAX(s);
+    const int lmax = HT::REG ? SONIC_MXORDS + 1 : SONIC_LMAX(s);
     s.ialth--;
     if (s.ialth == 0) {
         if (l != lmax) {
@@ -1446,7 +1563,8 @@ SONIC_HD void sonic_after_accept(SonicLane& s, const SonicHist& H, const SonicTa
 
 // Emit every output sample reached by the accepted step; end-of-cycle logic (solvers.py:317-365).
 // begin_mode: 2 = go on with the next step, 0 = a new cycle (or nothing) has been set up.
-SONIC_HD void sonic_emit(SonicLane& s, const SonicHist& H, const SonicSink& sink, double period, int& begin_mode) {
+template <class HT>
+SONIC_HD void sonic_emit(SonicLane& s, HT& H, const SonicSink& sink, double period, int& begin_mode) {
     begin_mode = 2;
     while ((s.tn - s.tout) * s.h >= 0.0) {
         double yo[3];
@@ -1485,7 +1603,7 @@ SONIC_HD void sonic_emit(SonicLane& s, const SonicHist& H, const SonicSink& sink
             } else {
                 sink.zbuf[0] = yo[1];
                 sink.ngbuf[0] = yo[2];
-                sonic_cycle_begin(s, H, sink, s.tstop, period, yo);
+                sonic_cycle_begin(s, H.store(), sink, s.tstop, period, yo);
             }
             break;
         }
@@ -1501,7 +1619,8 @@ SONIC_HD void sonic_emit(SonicLane& s, const SonicHist& H, const SonicSink& sink
 
 // Preliminaries of the next step (begin_mode 1 = first step of a problem, 2 = after a success).
 // Returns true when the step can be predicted.
-SONIC_HD bool sonic_begin_step(SonicLane& s, const SonicHist& H, const SonicTables* T, int begin_mode) {
+template <class HT>
+SONIC_HD bool sonic_begin_step(SonicLane& s, HT& H, const SonicTables* T, int begin_mode) {
     if (begin_mode == 2) {
         if (s.nst - s.nslast >= SONIC_MXSTEP) {
             sonic_fail(s, SONIC_ST_MXSTEP);
@@ -1640,17 +1759,76 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     if (do_predict) sonic_predict(s, H);
 }
 
-// Nested driver of the same tick, for a lane that is alone in its warp: no stage flags, every lane
-// state follows its own path and leaves as soon as its next evaluation point is set.  Same pieces,
-// same order, same arithmetic as sonic_tick.
+// ---------------------------------------------------------------------------------------
+// Nested driver of the same tick, for a lane that is alone in its warp: no stage flags, the lane follows
+// its own path and leaves as soon as its next evaluation point is set.  Same pieces, same order, same
+// arithmetic as sonic_tick.  The tick is cut in three: the head (consume the right-hand side, corrector,
+// error test), the tail of a failed step and the tail of an accepted one, the latter enterable after the
+// method-switch test, after the order selection, or from its start -- so that the register-resident run
+// below (sonic_fixed_order_run) can hand the rest of a tick over to these generic tails.
+// ---------------------------------------------------------------------------------------
+struct SonicLoneCarry {
+    bool corr_failed;
+    int sel_mode;
+    double sel_rhup;
+    SonicStepCtx ctx;
+    SonicRescaleReq rq;
+};
+
+SONIC_HD void sonic_carry_reset(SonicLoneCarry& c) {
+    c.corr_failed = false;
+    c.sel_mode = 0;
+    c.sel_rhup = 0.0;
+    c.ctx.pw_fast = c.ctx.pw_exact = NAN;
+    c.rq.pending = false; c.rq.rmax10 = false; c.rq.rh = 1.0;
+}
+
+// Tail of a failed step (corrector failure with a current Jacobian, or error test failed).
+SONIC_HD void sonic_lone_failed_tail(SonicLane& s, const SonicHist& H, const SonicTables* T, SonicLoneCarry& c) {
+    bool do_predict = false;
+    sonic_retract(s, H, c.corr_failed, do_predict, c.sel_mode, c.rq);
+    if (c.sel_mode == 2) {
+        sonic_select(s, H, T, 0.0, 2, &c.ctx, c.rq);
+        do_predict = true;
+    }
+    if (c.rq.pending) {
+        sonic_rescale(s, H, T, c.rq.rh);
+        if (c.rq.rmax10) s.rmax = 10.0;
+    }
+    if (do_predict) sonic_predict(s, H);
+}
+
+// Tail of an accepted step, from `entry`:
+//   0 = from the start (history update, method-switch test, step/order bookkeeping, selection)
+//   1 = after a method switch has been made          2 = the order selection is due (c.sel_mode, c.sel_rhup)
+//   3 = after the order selection (a rescale may be pending)
+enum { SONIC_TAIL_START = 0, SONIC_TAIL_SWITCHED = 1, SONIC_TAIL_SELECT = 2, SONIC_TAIL_SELECTED = 3 };
+SONIC_HD void sonic_lone_accepted_tail(SonicLane& s, const SonicHist& H, const SonicTables* T, const SonicSink& sink,
+                                       double period, SonicLoneCarry& c, int entry) {
+    if (entry == SONIC_TAIL_START) {
+        bool switched = false;
+        if (sonic_accept(s, H, T)) switched = sonic_method_switch(s, H, T, &c.ctx, c.rq);
+        if (!switched) {
+            sonic_after_accept(s, H, T, c.sel_mode, c.sel_rhup);
+            if (c.sel_mode != 0) entry = SONIC_TAIL_SELECT;
+        }
+    }
+    if (entry == SONIC_TAIL_SELECT) sonic_select(s, H, T, c.sel_rhup, 0, &c.ctx, c.rq);
+    if (s.meth != s.mused) s.jstart = -1;             // method switch: reload coefficients
+    if (c.rq.pending) {
+        sonic_rescale(s, H, T, c.rq.rh);
+        if (c.rq.rmax10) s.rmax = 10.0;
+    }
+    int begin_mode;
+    sonic_emit(s, H, sink, period, begin_mode);
+    if (begin_mode != 0 && sonic_begin_step(s, H, T, begin_mode)) sonic_predict(s, H);
+}
+
 SONIC_HD void sonic_tick_lone(SonicLane& s, const SonicHist& H, const SonicTables* T,
                               const SonicPoint& p, const SonicSink& sink, double period,
                               const double f[3]) {
     s.nfe++;
-    bool converged = false, corr_failed = false, do_predict = false;
-    int sel_mode = 0;
-    SonicRescaleReq rq;
-    rq.pending = false; rq.rmax10 = false; rq.rh = 1.0;
+    bool converged = false, corr_failed = false;
     const int phase = s.phase;
     if (phase == PH_CORR_FIRST || phase == PH_CORR_ITER) {
         s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
@@ -1675,8 +1853,6 @@ SONIC_HD void sonic_tick_lone(SonicLane& s, const SonicHist& H, const SonicTable
         return;
     }
     if (!converged && !corr_failed) return;           // one more corrector iterate at (tn, y)
-    SonicStepCtx ctx;
-    ctx.pw_fast = ctx.pw_exact = NAN;
     bool failed = corr_failed;                        // a path that retracts the step
     if (corr_failed) {
         if (s.miter != 0 && s.jcur != 1) {
@@ -1686,35 +1862,122 @@ SONIC_HD void sonic_tick_lone(SonicLane& s, const SonicHist& H, const SonicTable
     } else {
         failed = sonic_error_test(s, T);
     }
-    if (failed) {
-        sonic_retract(s, H, corr_failed, do_predict, sel_mode, rq);
-        if (sel_mode == 2) {
-            sonic_select(s, H, T, 0.0, 2, &ctx, rq);
-            do_predict = true;
+    SonicLoneCarry c;
+    sonic_carry_reset(c);
+    c.corr_failed = corr_failed;
+    if (failed) sonic_lone_failed_tail(s, H, T, c);
+    else sonic_lone_accepted_tail(s, H, T, sink, period, c, SONIC_TAIL_START);
+}
+
+// ---------------------------------------------------------------------------------------
+// Register-resident run in the BDF family.
+//
+// The chains that bound a lookup's wall time (up to 7e5 dependent right-hand sides for one grid point)
+// spend 99 % of their steps in the BDF family (orders 1-5).  While a lane stays there its Nordsieck
+// columns live in registers (SonicRegHist) and it loops here over right-hand side -> corrector -> error
+// test -> history update -> method-switch test -> order selection -> output samples -> prediction
+// without going back to the caller: no indexed shared-memory traffic for the history, no phase
+// dispatch.  Whatever is rare (a failed step, a method switch, the end of a cycle) writes the columns
+// back and returns the point of the tick at which the generic tails above take over; the arithmetic is
+// that of sonic_tick_lone, operation for operation.
+//
+// Returns: 0 = the tick is complete (the lane's next evaluation point is set, or the lane is done),
+//          1 = failed step: call sonic_lone_failed_tail,  2 + entry = call sonic_lone_accepted_tail(entry).
+// ---------------------------------------------------------------------------------------
+template <bool OVT>
+SONIC_HD int sonic_bdf_run(SonicLane& s, const SonicHist& Hs, const SonicTables* T, SonicPoint& p,
+                           const SonicSink& sink, double period, SonicLoneCarry& c) {
+    SonicRegHist R;
+    R.S = Hs;
+    R.load();
+    int resume = 0;
+    while (true) {
+        SONIC_ASSUME(s.tab_meth == 2);
+        SONIC_ASSUME(s.nq >= 1 && s.nq <= SONIC_MXORDS);
+        double f[3];
+        if (OVT) sonic_update_charge(p, s.tn);
+        if (sonic_rhs(p, s.tn, s.y, f)) s.status |= SONIC_ST_ZCLAMP;
+        s.nfe++;
+        bool converged = false, corr_failed = false;
+        bool run_corrector = true;
+        if (s.phase == PH_JAC) {
+            if (!sonic_jac_consume(s, Hs, p, f)) {
+                corr_failed = true;
+                run_corrector = false;
+            }
+        } else {
+            s.savf[0] = f[0]; s.savf[1] = f[1]; s.savf[2] = f[2];
+            if (s.phase == PH_CORR_FIRST) {
+                if (s.ipup > 0) {
+                    sonic_jac_setup(s);
+                    continue;
+                }
+                s.acor[0] = s.acor[1] = s.acor[2] = 0.0;
+            }
         }
-        if (rq.pending) {
-            sonic_rescale(s, H, T, rq.rh);
-            if (rq.rmax10) s.rmax = 10.0;
+        if (run_corrector) sonic_corrector(s, R, T, converged, corr_failed);
+        if (!converged && !corr_failed) continue;         // one more corrector iterate at (tn, y)
+        bool failed = corr_failed;
+        if (corr_failed) {
+            if (s.miter != 0 && s.jcur != 1) {
+                sonic_retry_with_jacobian(s, R);
+                continue;
+            }
+        } else {
+            failed = sonic_error_test(s, T);
         }
-        if (do_predict) sonic_predict(s, H);
+        sonic_carry_reset(c);
+        c.corr_failed = corr_failed;
+        if (failed) {
+            resume = 1;
+            break;
+        }
+        // accepted step
+        if (sonic_accept(s, R, T)) {
+            if (sonic_method_switch(s, Hs, T, &c.ctx, c.rq)) {
+                resume = 2 + SONIC_TAIL_SWITCHED;
+                break;
+            }
+        }
+        sonic_after_accept(s, R, T, c.sel_mode, c.sel_rhup);
+        if (c.sel_mode != 0) {
+            sonic_select(s, R, T, c.sel_rhup, 0, &c.ctx, c.rq);
+            if (c.rq.pending) {
+                sonic_rescale(s, R, T, c.rq.rh);
+                if (c.rq.rmax10) s.rmax = 10.0;
+            }
+        }
+        int begin_mode;
+        sonic_emit(s, R, sink, period, begin_mode);
+        if (begin_mode == 0) break;                       // a new cycle has been set up, or the lane is done
+        if (!sonic_begin_step(s, R, T, begin_mode)) break;
+        sonic_predict(s, R);
+    }
+    R.spill();
+    return resume;
+}
+
+// Can the lane enter the register-resident run?  (a step in progress in the BDF family, coefficients loaded)
+SONIC_HD bool sonic_bdf_run_ok(const SonicLane& s) {
+    return s.meth == 2 && s.tab_meth == 2 &&
+           (s.phase == PH_CORR_FIRST || s.phase == PH_CORR_ITER || s.phase == PH_JAC);
+}
+
+// Advance a lone lane: as many ticks as the register-resident run can take, or one generic tick.
+template <bool OVT>
+SONIC_HD void sonic_lone_advance(SonicLane& s, const SonicHist& H, const SonicTables* T, SonicPoint& p,
+                                 const SonicSink& sink, double period) {
+    if (sonic_bdf_run_ok(s)) {
+        SonicLoneCarry c;
+        const int r = sonic_bdf_run<OVT>(s, H, T, p, sink, period, c);
+        if (r == 1) sonic_lone_failed_tail(s, H, T, c);
+        else if (r >= 2) sonic_lone_accepted_tail(s, H, T, sink, period, c, r - 2);
         return;
     }
-    // accepted step
-    bool switched = false;
-    if (sonic_accept(s, H, T)) switched = sonic_method_switch(s, H, T, &ctx, rq);
-    if (!switched) {
-        double sel_rhup = 0.0;
-        sonic_after_accept(s, H, T, sel_mode, sel_rhup);
-        if (sel_mode != 0) sonic_select(s, H, T, sel_rhup, 0, &ctx, rq);
-    }
-    if (s.meth != s.mused) s.jstart = -1;             // method switch: reload coefficients
-    if (rq.pending) {
-        sonic_rescale(s, H, T, rq.rh);
-        if (rq.rmax10) s.rmax = 10.0;
-    }
-    int begin_mode;
-    sonic_emit(s, H, sink, period, begin_mode);
-    if (begin_mode != 0 && sonic_begin_step(s, H, T, begin_mode)) sonic_predict(s, H);
+    double f[3];
+    if (OVT) sonic_update_charge(p, s.tn);
+    if (sonic_rhs(p, s.tn, s.y, f)) s.status |= SONIC_ST_ZCLAMP;
+    sonic_tick_lone(s, H, T, p, sink, period, f);
 }
 
 // Start a lane on its grid point with a precomputed initial deflection.

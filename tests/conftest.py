@@ -64,6 +64,11 @@ class HostSim:
     def _bls(self, b):
         return np.array([b.a, b.Delta, b.x0, b.C, b.nrep, b.nattr, b.Cm0, 0.0])
 
+    def set_driver(self, d):
+        ''' 0 = staged tick (wide warps), 1 = nested tick of a lone lane, 2 = lone lane with register-resident
+            BDF runs (sonic_lone_advance) '''
+        self.lib.hostsim_set_driver(ctypes.c_int(d))
+
     def point(self, b, f, A, Q, trace=False, overtones=None):
         ''' overtones: list of (amplitude C/m2, phase rad) pairs (nbls.py:169-178) '''
         if overtones:

@@ -13,7 +13,7 @@
 static SonicTables g_tab;
 static int g_tab_ready = 0;
 
-static int g_driver = 0;   // 0 = staged tick (sonic_tick), 1 = nested tick of a lone lane (sonic_tick_lone)
+static int g_driver = 0;   // 0 = staged tick (sonic_tick), 1 = nested tick of a lone lane (sonic_tick_lone), 2 = sonic_lone_advance
 static double* g_steplog = 0;
 static long g_steplog_max = 0, g_steplog_n = 0;
 
@@ -62,6 +62,14 @@ long hostsim_point_ov(const double* bls, double f, double A, double Q, int nov, 
     int cyc0 = 0, k0 = 1;
     unsigned nfe_base = 0, nje_base = 0;
     while (s.phase != PH_DONE) {
+        if (g_driver == 2) {
+            // register-resident runs at fixed order + generic lone ticks (several ticks per call: no per-tick logs)
+            const unsigned before = s.nfe - 2 * s.nje;
+            if (p.nov) sonic_lone_advance<true>(s, H, &g_tab, p, sink, period);
+            else sonic_lone_advance<false>(s, H, &g_tab, p, sink, period);
+            nticks += (long)((s.nfe - 2 * s.nje) - before);
+            continue;
+        }
         double fv[3];
         if (p.nov) sonic_update_charge(p, s.tn);
         if (sonic_rhs(p, s.tn, s.y, fv)) s.status |= SONIC_ST_ZCLAMP;

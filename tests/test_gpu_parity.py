@@ -465,6 +465,43 @@ def test_plan_relaunch_is_deterministic(gpu):
         assert np.mean(Vm) == pytest.approx(out2[0][0, i, 0], rel=1e-12)
 
 
+def test_lone_run_and_staged_tick_are_bit_identical(gpu, monkeypatch):
+    ''' A point integrated by a lane alone in its warp (register-resident BDF runs + nested ticks: small
+        batches, and the longest chains of a large grid) and by the staged tick of a wide warp must come out
+        bit for bit the same: tables, cycle counts, status and right-hand-side counts.  SONIC_NESTED=0 (read
+        when a plan is created) forces the staged tick everywhere. '''
+    ps = _ps()
+    pn = ps.getPointNeuron('RS')
+    radii = [ps.NeuronalBilayerSonophore(a, pn).abi_params() for a in (16e-9, 32e-9, 64e-9)]
+    rng = np.random.default_rng(11)
+    n = 96                                       # fewer points than warps: one point per warp, lone lanes
+    ia = rng.integers(0, 3, n).astype(np.int32)
+    f = rng.choice([20e3, 100e3, 500e3, 1e6, 4e6], n)
+    A = 10 ** rng.uniform(2, 5.78, n)
+    Q = rng.uniform(-107e-5, 50e-5, n)
+    ov = np.zeros((n, 1, 2))
+    ov[:, 0, 0] = rng.uniform(0, 5e-5, n)
+    ov[:, 0, 1] = rng.uniform(-np.pi, np.pi, n)
+    for overtones in (None, ov):
+        res = []
+        for nested in (None, '0'):
+            if nested is None:
+                monkeypatch.delenv('SONIC_NESTED', raising=False)
+            else:
+                monkeypatch.setenv('SONIC_NESTED', nested)
+            plan = gpu.Plan(0, radii, pn.neuron_id, len(pn.rates), ia, f, A, Q, np.array([1.0]), overtones=overtones)
+            plan.launch()
+            res.append(plan.fetch())
+            plan.destroy()
+        monkeypatch.delenv('SONIC_NESTED', raising=False)
+        (out1, nc1, st1, _, nr1), (out2, nc2, st2, _, nr2) = res
+        np.testing.assert_array_equal(nc1, nc2)
+        np.testing.assert_array_equal(st1, st2)
+        np.testing.assert_array_equal(nr1, nr2)
+        assert out1.tobytes() == out2.tobytes()
+        assert (nc1 >= 2).all()
+
+
 def test_cm_lookup(gpu, tmp_path):
     ''' computeCmLookup (scripts/run_Cm_lookups.py:19-64) against profiles
         produced by the reference, sample by sample, and its on-disk format. '''

@@ -261,3 +261,36 @@ def test_qags_restatement_is_bitwise_scipy_quad(hostsim, points_golden):
         assert abs(out[0] - r['PMavg']) <= 9e-16 * abs(r['PMavg']), r       # bit-identical but for one value (1 ulp)
         nlast.add(int(last[0]))
     assert len(nlast) >= 2          # accepted at the first rule for some deflections, bisected for others
+
+
+def test_tick_drivers_are_bit_identical(hostsim):
+    ''' The three drivers of the lane state machine -- staged tick (wide warps), nested tick (a lane alone in
+        its warp) and the register-resident BDF run with the generic tails around it -- are built from the same
+        pieces and must give the same bits: profiles, cycle counts, status and every counter. '''
+    rng = np.random.default_rng(7)
+    cases = [(16e-9, 20e3, 5e3, -106e-5), (32e-9, 500e3, 600e3, -80e-5), (64e-9, 4e6, 300e3, -50e-5),
+             (32e-9, 500e3, 0.0, -70e-5), (16e-9, 20e3, 600e3, 50e-5), (32e-9, 500e3, 80e3, 0.0)]
+    for _ in range(18):
+        cases.append((float(rng.choice([16e-9, 32e-9, 64e-9])), float(rng.choice([20e3, 100e3, 500e3, 1e6, 4e6])),
+                      float(10 ** rng.uniform(2, 5.78)), float(rng.uniform(-107e-5, 50e-5))))
+    bls = {a: so.get_bls('RS', a) for a in (16e-9, 32e-9, 64e-9)}
+    try:
+        for a, f, A, Q in cases:
+            res = []
+            for drv in (0, 1, 2):
+                hostsim.set_driver(drv)
+                res.append(hostsim.point(bls[a], f, A, Q))
+            for r in res[1:]:
+                assert r['z'].tobytes() == res[0]['z'].tobytes() and r['ng'].tobytes() == res[0]['ng'].tobytes(), (a, f, A, Q)
+                for k in ('ncycles', 'status', 'nfe', 'nje', 'nsteps'):
+                    assert r[k] == res[0][k], (k, a, f, A, Q)
+        # and with charge overtones (the right-hand side refreshes the imposed charge on its own clock)
+        ov = [(8e-5, 0.3)]
+        res = []
+        for drv in (0, 1, 2):
+            hostsim.set_driver(drv)
+            res.append(hostsim.point(bls[32e-9], 500e3, 100e3, -40e-5, overtones=ov))
+        for r in res[1:]:
+            assert r['z'].tobytes() == res[0]['z'].tobytes() and r['nfe'] == res[0]['nfe'] and r['ncycles'] == res[0]['ncycles']
+    finally:
+        hostsim.set_driver(0)

@@ -90,7 +90,7 @@ def ncu_full(tag):
                 nticks = str(json.loads(ln)['roofline']['rhs_evaluations'])
     sass = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'sass_profile.py'), rep,
                            os.path.join(ROOT, 'pysonic_b200', 'libsonic_b200.so'),
-                           '_Z22sonic_integrate_kernel8SonicJob', nticks], capture_output=True, text=True).stdout
+                           '_Z22sonic_integrate_kernelILb0EEv8SonicJob', nticks], capture_output=True, text=True).stdout
     with open(os.path.join(PROF, f'{tag}_sass_profile.txt'), 'w') as fh:
         fh.write('# executed warp-instructions per source function of sonic_integrate_kernel (ncu source page x nvdisasm line info)\n')
         fh.write('\n'.join(sass.splitlines()[:45]) + '\n')
@@ -112,6 +112,69 @@ def c2_counters(tag):
         return float(vals['dram__bytes_read.sum'][0].replace(',', '')) + float(vals['dram__bytes_write.sum'][0].replace(',', ''))
     except KeyError:
         return None
+
+
+def workload_counters(tag):
+    ''' integrator / averaging counters of the C3 (STN), C4 (SWnode) and C5 (TC) workloads. '''
+    with open(os.path.join(PROF, f'{tag}_ncu_workloads.txt'), 'w') as fh:
+        fh.write('# ncu --metrics ... -k regex:"sonic_integrate|sonic_average"  python tools/gpu_workload.py <W>\n')
+        for w in ('STN', 'SWnode', 'TC'):
+            path = os.path.join(OUT, f'counters_{w}_{tag}.csv')
+            if not os.path.isfile(path):
+                continue
+            rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+            hdr = rows[0]
+            ik, ii = hdr.index('Kernel Name'), hdr.index('ID')
+            im, iu, iv = hdr.index('Metric Name'), hdr.index('Metric Unit'), hdr.index('Metric Value')
+            plain = os.path.join(OUT, f'plain_{w}_{tag}.log')
+            if os.path.isfile(plain):
+                fh.write(f'## {w}: ' + open(plain).read().strip().splitlines()[-1] + '\n')
+            last = None
+            for r in rows[1:]:
+                if (r[ii], r[ik]) != last:
+                    last = (r[ii], r[ik])
+                    fh.write(f'kernel {r[ik][:60]} (launch {r[ii]})\n')
+                fh.write(f'  {r[im]:70s} {r[iv]:>18s} {r[iu]}\n')
+
+
+def avg_full(tag):
+    rep = os.path.join(OUT, f'prof_avg_stn_{tag}.ncu-rep')
+    if not os.path.isfile(rep):
+        return
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    keys = KEYS + ['l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+                   'smsp__sass_average_data_bytes_per_sector_mem_global_op_st.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+                   'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed']
+    with open(os.path.join(PROF, f'{tag}_ncu_average_stn.txt'), 'w') as fh:
+        fh.write('# ncu --set full --clock-control none --import-source on -k regex:sonic_average -c 1  python tools/gpu_workload.py STN\n')
+        fh.write('# (C3 shape: STN, 7 344 trajectories x 100 coverage fractions x 19 tables)\n')
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            fh.write(f'kernel: {d["Kernel Name"]}\n')
+            for k in keys:
+                if k in d:
+                    fh.write(f'  {k:70s} {d[k]:>18s} {units[hdr.index(k)]}\n')
+            st = {k: float(v.replace(',', '')) for k, v in d.items()
+                  if 'pcsamp_warps_issue_stalled' in k and 'not_issued' not in k and v not in ('', 'n/a')}
+            tot = sum(st.values()) or 1
+            fh.write('  warp stall reasons (pc sampling):\n')
+            for k, v in sorted(st.items(), key=lambda x: -x[1])[:6]:
+                fh.write(f'    {k.replace("smsp__pcsamp_warps_issue_stalled_", ""):30s} {100 * v / tot:6.1f} %\n')
+
+
+def extras(tag):
+    ''' parity report, workload probes, kernel probe: small JSON files copied as they are. '''
+    import shutil
+    for src, dst in ((f'parity_{tag}.json', f'{tag}_parity.json'), (f'configs_{tag}.json', f'{tag}_configs_c3_c4_c5.json'),
+                     (f'offnode_{tag}.json', f'{tag}_offnode.json'), (f'overtones_{tag}.json', f'{tag}_overtones_lookup.json'),
+                     (f'kprobe_{tag}.json', f'{tag}_kprobe.json')):
+        p = os.path.join(OUT, src)
+        if os.path.isfile(p) and os.path.getsize(p) > 0:
+            shutil.copyfile(p, os.path.join(PROF, dst))
+    workload_counters(tag)
+    avg_full(tag)
 
 
 def main():
@@ -139,6 +202,7 @@ def main():
             if os.path.isfile(p):
                 with open(p) as src, open(os.path.join(PROF, f'{tag}_{f}.txt'), 'w') as dst:
                     dst.write(''.join(src.readlines()[-15:]))
+    extras(tag)
     print('profiles/:', sorted(x for x in os.listdir(PROF) if x.startswith(tag)))
 
 
