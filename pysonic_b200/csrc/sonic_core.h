@@ -472,8 +472,20 @@ SONIC_HD double sonic_pg(const SonicPoint& p, double Z, double ng) {
 #endif
 }
 
-// Right-hand side (bls.py:681-718).  Returns true if the Zmin clamp was applied.
-SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double dy[3]) {
+// Sine of the drive at time t (drives.py:303-304 with phi = pi); the acoustic pressure is A times this.
+SONIC_HD double sonic_drive(const SonicPoint& p, double t) {
+#ifdef SONIC_EXACT_MATH
+    return sin(p.omega * t - SONIC_PI);
+#else
+    return sonic_sin_drive(p.f * t);
+#endif
+}
+
+// Right-hand side (bls.py:681-718) for a given drive sine sd = sonic_drive(p, t).  Returns true if the Zmin
+// clamp was applied.  (The product A sd is formed here, next to the sum it enters: the device compiler contracts the
+// two into one fused operation, and every caller must get the same one.)
+SONIC_HD bool sonic_rhs_pac(const SonicPoint& p, const double sd, const double y[3], double dy[3]) {
+    const double Pac = p.A * sd;
     const double U = y[0];
     double Z = y[1];
     const double ng = y[2];
@@ -488,11 +500,6 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     const double ainvR = fabs(invR);
     const double Pg = sonic_pg(p, Z, ng);
     const double Pm = sonic_pm(p, Z);
-#ifdef SONIC_EXACT_MATH
-    const double Pac = p.A * sin(p.omega * t - SONIC_PI);             // drives.py:303-304
-#else
-    const double Pac = p.A * sonic_sin_drive(p.f * t);
-#endif
     const double Pv = -12.0 * U * SONIC_DELTA0 * SONIC_MUS * (invR * invR)
                       - 4.0 * U * SONIC_MUL * ainvR;                  // bls.py:613-631
 #ifdef SONIC_EXACT_MATH
@@ -508,6 +515,10 @@ SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double
     dy[2] = SONIC_DIVC(2.0 * (SONIC_PI * s2) * SONIC_DGL * (SONIC_C0 - SONIC_DIVC(Pg, SONIC_KH)),
                        SONIC_XI);                                    // bls.py:508-516
     return clamped;
+}
+
+SONIC_HD bool sonic_rhs(const SonicPoint& p, double t, const double y[3], double dy[3]) {
+    return sonic_rhs_pac(p, sonic_drive(p, t), y, dy);
 }
 
 // Refresh the electrical pressure factor Q(t)^2 / (2 eps0) of a point with charge overtones.
@@ -1226,6 +1237,14 @@ SONIC_HD bool sonic_method_switch_decide(const SonicLane& s, const SonicTables* 
         return true;
     }
     // currently BDF (nq <= 5 <= MXORDN): consider Adams at the same order
+    {
+        // Stiff at this step size?  The Adams candidate is bounded by its stability limit, rh1 <= sm1 / pdh (or, when
+        // pdh rh1 <= 1e-5, rh1 <= 1e-5 / pdh < 4e-4), while the error test just passed (dsm <= 1) puts the BDF
+        // candidate at rh2 >= 1 / 1.2000012: with sm1 < 0.8 pdh the test below cannot but say "stay", whatever the
+        // powers are -- the common case on this path, settled without them.
+        const double pdh0 = s.pdnorm * fabs(s.h);
+        if (s.dsm <= 1.0 && T->sm1[s.nq - 1] < 0.8 * pdh0) return false;
+    }
     const double c21 = T->c21[s.nq - 1];
     double dm1 = s.dsm * c21;
     double rh1 = sonic_rcp(1.2 * sonic_powr_scaled(s.dsm, c21, T->c21e[s.nq - 1], exsm, s.nq + 1, ctx, exact) + 0.0000012);
@@ -1428,7 +1447,7 @@ SONIC_HD void sonic_corrector(SonicLane& s, HT& H, const SonicTables* T, bool& c
 #endif
         const double dcon = SONIC_QUOT(s.del * fmin(1.0, 1.5 * s.crate), SONIC_TESCO(s, T, 1) * s.conit, SONIC_RCON(s, T));
         if (dcon <= 1.0) {
-            s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));
+            if (s.rate != 0.0) s.pdest = fmax(s.pdest, sonic_div(s.rate, fabs(s.h * el1)));   // (pdest >= 0)
             if (s.pdest != 0.0) s.pdlast = s.pdest;
             converged = true;
         }
@@ -1891,12 +1910,16 @@ SONIC_HD int sonic_bdf_run(SonicLane& s, const SonicHist& Hs, const SonicTables*
     R.S = Hs;
     R.load();
     int resume = 0;
+    // the drive pressure is evaluated once per step: the corrector iterates and the Jacobian column are taken at the
+    // same time as the first evaluation
+    double pac = sonic_drive(p, s.tn);
     while (true) {
         SONIC_ASSUME(s.tab_meth == 2);
         SONIC_ASSUME(s.nq >= 1 && s.nq <= SONIC_MXORDS);
         double f[3];
         if (OVT) sonic_update_charge(p, s.tn);
-        if (sonic_rhs(p, s.tn, s.y, f)) s.status |= SONIC_ST_ZCLAMP;
+        if (s.phase == PH_CORR_FIRST) pac = sonic_drive(p, s.tn);
+        if (sonic_rhs_pac(p, pac, s.y, f)) s.status |= SONIC_ST_ZCLAMP;
         s.nfe++;
         bool converged = false, corr_failed = false;
         bool run_corrector = true;
