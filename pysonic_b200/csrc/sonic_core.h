@@ -122,6 +122,9 @@ struct SonicTables {
     double rcon[2][12];        // 1 / (tesco[.][q][1] * conit(q)), conit(q) = 0.5 / (q + 2)
     double c21e[5];            // (cm2[q] / cm1[q])^(1 / (q + 2)): ratio of the two families' error constants,
     double c12e[5];            // (cm1[q] / cm2[q])^(1 / (q + 2))  raised to the step-size exponent of order q + 1
+    // error levels above which a step-size candidate of BDF order q + 1 is certainly below 1.1 (sonic_select):
+    // same order (1 / (1.2 d^(1/(q+2)) + 1.2e-6)), one order down (1.3, exponent 1/(q+1)), one order up (1.4, 1/(q+3))
+    double thr_sm[5], thr_dn[5], thr_up[5];
 };
 
 // Per-radius constants (one entry per sonophore radius of the lookup).
@@ -1135,14 +1138,28 @@ SONIC_HD double sonic_rhsm0(const SonicLane& s, const SonicTables* T, SonicStepC
 // Choose the next order/step after a success (ialth == 0, iredo = 0) or an error-test failure
 // (iredo = 2).  Returns true if the step must be redone (predict again).  Sets the step size: exact powers.
 template <class HT>
-SONIC_HD bool sonic_select(SonicLane& s, HT& H, const SonicTables* T, double rhup,
+SONIC_HD bool sonic_select(SonicLane& s, HT& H, const SonicTables* T, double dup,
                            int iredo, SonicStepCtx* ctx, SonicRescaleReq& rq) {
     const int l = s.nq + 1;
     const int lmax = HT::REG ? SONIC_MXORDS + 1 : SONIC_LMAX(s);
+    double ddn = 0.0;
+    if (s.nq != 1) ddn = SONIC_QUOT(sonic_mnorm_col(H, l - 1, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
+    if (s.meth == 2 && iredo == 0 && s.kflag == 0) {
+        // After a successful BDF step every branch below ends in "change the step only if the chosen ratio is at least
+        // 1.1".  If each of the three candidates is certainly below 1.1 -- its error estimate above the tabulated level --
+        // nothing changes whichever is the largest, and none of the three powers is needed (most selections end here).
+        if (s.dsm > T->thr_sm[s.nq - 1] && (s.nq == 1 || ddn > T->thr_dn[s.nq - 1]) &&
+            (dup < 0.0 || dup > T->thr_up[s.nq - 1])) {
+            s.ialth = 3;
+            return false;
+        }
+    }
+    // candidate for an order increase (none at the maximum order, or when called after a failed error test)
+    double rhup = 0.0;
+    if (dup >= 0.0) rhup = sonic_rcp(1.4 * sonic_powr(dup, T->rk[l + 1], l + 1) + 0.0000014);
     double rhsm = sonic_rhsm0(s, T, ctx, true);
     double rhdn = 0.0;
     if (s.nq != 1) {
-        const double ddn = SONIC_QUOT(sonic_mnorm_col(H, l - 1, s.ewt), SONIC_TESCO(s, T, 0), SONIC_RTESCO(s, T, 0));
         const double exdn = T->rk[s.nq];
         rhdn = sonic_rcp(1.3 * sonic_powr(ddn, exdn, s.nq) + 0.0000013);
     }
@@ -1556,10 +1573,11 @@ SONIC_HD bool sonic_accept(SonicLane& s, HT& H, const SonicTables* T) {
 }
 
 // Step/order bookkeeping after a success without method switch: every ialth steps prepare the
-// order/step selection (sel_mode = 1, candidate for an order increase in sel_rhup).
+// order/step selection (sel_mode = 1, scaled error estimate of the next higher order in sel_dup, negative when
+// there is none).
 template <class HT>
 SONIC_HD void sonic_after_accept(SonicLane& s, HT& H, const SonicTables* T, int& sel_mode,
-                                 double& sel_rhup) {
+                                 double& sel_dup) {
     const int l = s.nq + 1;
     const int lmax = HT::REG ? SONIC_MXORDS + 1 : SONIC_LMAX(s);
     s.ialth--;
@@ -1568,9 +1586,7 @@ SONIC_HD void sonic_after_accept(SonicLane& s, HT& H, const SonicTables* T, int&
             const double dup0 = sonic_mnorm3(s.acor[0] - H.yh(lmax - 1, 0),
                                             s.acor[1] - H.yh(lmax - 1, 1),
                                             s.acor[2] - H.yh(lmax - 1, 2), s.ewt);
-            const double dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
-            const double exup = T->rk[l + 1];
-            sel_rhup = sonic_rcp(1.4 * sonic_powr(dup, exup, l + 1) + 0.0000014);
+            sel_dup = SONIC_QUOT(dup0, SONIC_TESCO(s, T, 2), SONIC_RTESCO(s, T, 2));
         }
         sel_mode = 1;
     } else if (s.ialth <= 1 && l != lmax) {
@@ -1731,7 +1747,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
         else cf_retract = true;
     }
     int sel_mode = 0;          // 1 = order/step selection after a success, 2 = after a failure
-    double sel_rhup = 0.0;
+    double sel_dup = -1.0;
     SonicStepCtx ctx;
     ctx.pw_fast = ctx.pw_exact = NAN;
     SonicRescaleReq rq;
@@ -1748,11 +1764,11 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
     if (do_mswitch) switched = sonic_method_switch(s, H, T, &ctx, rq);
 
     // ---- stage C3: step/order bookkeeping after a success ---------------------------------
-    if (accepted && !switched) sonic_after_accept(s, H, T, sel_mode, sel_rhup);
+    if (accepted && !switched) sonic_after_accept(s, H, T, sel_mode, sel_dup);
 
     // ---- stage C4: order and step-size selection (after a success or a failed error test) -
     if (sel_mode != 0) {
-        const bool redo = sonic_select(s, H, T, sel_rhup, sel_mode == 2 ? 2 : 0, &ctx, rq);
+        const bool redo = sonic_select(s, H, T, sel_dup, sel_mode == 2 ? 2 : 0, &ctx, rq);
         if (sel_mode == 2) do_predict = true;
         (void)redo;
     }
@@ -1789,7 +1805,7 @@ SONIC_HD void sonic_tick(SonicLane& s, const SonicHist& H, const SonicTables* T,
 struct SonicLoneCarry {
     bool corr_failed;
     int sel_mode;
-    double sel_rhup;
+    double sel_dup;
     SonicStepCtx ctx;
     SonicRescaleReq rq;
 };
@@ -1797,7 +1813,7 @@ struct SonicLoneCarry {
 SONIC_HD void sonic_carry_reset(SonicLoneCarry& c) {
     c.corr_failed = false;
     c.sel_mode = 0;
-    c.sel_rhup = 0.0;
+    c.sel_dup = -1.0;
     c.ctx.pw_fast = c.ctx.pw_exact = NAN;
     c.rq.pending = false; c.rq.rmax10 = false; c.rq.rh = 1.0;
 }
@@ -1807,7 +1823,7 @@ SONIC_HD void sonic_lone_failed_tail(SonicLane& s, const SonicHist& H, const Son
     bool do_predict = false;
     sonic_retract(s, H, c.corr_failed, do_predict, c.sel_mode, c.rq);
     if (c.sel_mode == 2) {
-        sonic_select(s, H, T, 0.0, 2, &c.ctx, c.rq);
+        sonic_select(s, H, T, -1.0, 2, &c.ctx, c.rq);
         do_predict = true;
     }
     if (c.rq.pending) {
@@ -1819,7 +1835,7 @@ SONIC_HD void sonic_lone_failed_tail(SonicLane& s, const SonicHist& H, const Son
 
 // Tail of an accepted step, from `entry`:
 //   0 = from the start (history update, method-switch test, step/order bookkeeping, selection)
-//   1 = after a method switch has been made          2 = the order selection is due (c.sel_mode, c.sel_rhup)
+//   1 = after a method switch has been made          2 = the order selection is due (c.sel_mode, c.sel_dup)
 //   3 = after the order selection (a rescale may be pending)
 enum { SONIC_TAIL_START = 0, SONIC_TAIL_SWITCHED = 1, SONIC_TAIL_SELECT = 2, SONIC_TAIL_SELECTED = 3 };
 SONIC_HD void sonic_lone_accepted_tail(SonicLane& s, const SonicHist& H, const SonicTables* T, const SonicSink& sink,
@@ -1828,11 +1844,11 @@ SONIC_HD void sonic_lone_accepted_tail(SonicLane& s, const SonicHist& H, const S
         bool switched = false;
         if (sonic_accept(s, H, T)) switched = sonic_method_switch(s, H, T, &c.ctx, c.rq);
         if (!switched) {
-            sonic_after_accept(s, H, T, c.sel_mode, c.sel_rhup);
+            sonic_after_accept(s, H, T, c.sel_mode, c.sel_dup);
             if (c.sel_mode != 0) entry = SONIC_TAIL_SELECT;
         }
     }
-    if (entry == SONIC_TAIL_SELECT) sonic_select(s, H, T, c.sel_rhup, 0, &c.ctx, c.rq);
+    if (entry == SONIC_TAIL_SELECT) sonic_select(s, H, T, c.sel_dup, 0, &c.ctx, c.rq);
     if (s.meth != s.mused) s.jstart = -1;             // method switch: reload coefficients
     if (c.rq.pending) {
         sonic_rescale(s, H, T, c.rq.rh);
@@ -1962,9 +1978,9 @@ SONIC_HD int sonic_bdf_run(SonicLane& s, const SonicHist& Hs, const SonicTables*
                 break;
             }
         }
-        sonic_after_accept(s, R, T, c.sel_mode, c.sel_rhup);
+        sonic_after_accept(s, R, T, c.sel_mode, c.sel_dup);
         if (c.sel_mode != 0) {
-            sonic_select(s, R, T, c.sel_rhup, 0, &c.ctx, c.rq);
+            sonic_select(s, R, T, c.sel_dup, 0, &c.ctx, c.rq);
             if (c.rq.pending) {
                 sonic_rescale(s, R, T, c.rq.rh);
                 if (c.rq.rmax10) s.rmax = 10.0;
@@ -2122,6 +2138,9 @@ static void sonic_fill_tables(SonicTables* T) {
     for (int i = 0; i < 5; i++) {
         T->c21e[i] = pow(T->c21[i], 1.0 / (i + 2));
         T->c12e[i] = pow(T->c12[i], 1.0 / (i + 2));
+        T->thr_sm[i] = pow((1.0 / 1.1 - 0.0000012) / 1.2, (double)(i + 2)) * (1.0 + 1e-9);
+        T->thr_dn[i] = pow((1.0 / 1.1 - 0.0000013) / 1.3, (double)(i + 1)) * (1.0 + 1e-9);
+        T->thr_up[i] = pow((1.0 / 1.1 - 0.0000014) / 1.4, (double)(i + 3)) * (1.0 + 1e-9);
     }
     for (int m = 0; m < 2; m++)
         for (int q = 0; q < 12; q++) {
