@@ -51,10 +51,10 @@
 #ifndef SONIC_WIDEN
 #define SONIC_WIDEN 1
 #endif
-/* relative to the tick of a lone lane in the register-resident run with four such warps on its SM (1.21 us): the same with
-   eight warps on the SM (1.63 us), and a lone lane of a staged warp among other staged warps (2.0 us) */
+/* relative to the tick of a lone lane in the register-resident run with four such warps on its SM (1.106 us): the same with
+   eight warps on the SM (1.44 us) */
 #ifndef SONIC_SCHED_LONE8_RATIO
-#define SONIC_SCHED_LONE8_RATIO 1.35
+#define SONIC_SCHED_LONE8_RATIO 1.30
 #endif
 /* the points of the full-width queue are short: start-up (initial deflection read, first Adams steps of every cycle) and
    partly empty warps make a lane-tick there cost more than in the calibration runs on long chains (5.5-7.5 us per
@@ -1242,17 +1242,20 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         for (int b = 0; b < (int)blocks; b++) border[b] = b;
         std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return smid[x] < smid[y]; });
         // Tick times, measured (tools/gpu_tk.py, tools/gpu_lone_rates.py: every warp of the device with k busy lanes on
-        // chains of the same kind), in units of t_f = 1.21 us, the tick of a lone lane in the register-resident run on an
-        // SM that hosts four such warps, one per scheduler: R8 = the same with eight warps on the SM (1.63 us), tk[k] = a
-        // staged warp with k busy lanes (1.89 us for k = 1, 2.57, 3.01, 3.33, ... 4.80 us for k = 32).
-        static const double tk_us[33] = {0, 1.885, 2.568, 3.013, 3.334, 3.56, 3.760, 3.91, 4.047, 4.13, 4.21, 4.28, 4.338,
-                                         4.38, 4.42, 4.46, 4.499, 4.53, 4.56, 4.59, 4.61, 4.64, 4.66, 4.69, 4.713, 4.73, 4.74,
-                                         4.75, 4.77, 4.78, 4.79, 4.80, 4.805};
+        // chains of the same kind), in units of t_f = 1.106 us, the tick of a lone lane in the register-resident run on an
+        // SM that hosts four such warps, one per scheduler: R8 = the same with eight warps on the SM (1.44 us), tk[k] = a
+        // staged warp with k busy lanes (1.65 us for k = 1, 2.25, 2.70, 3.05, ... 4.81 us for k = 32).
+        static const double tk_us[33] = {0, 1.645, 2.250, 2.701, 3.051, 3.32, 3.549, 3.73, 3.879, 3.99, 4.09, 4.18, 4.263,
+                                         4.33, 4.39, 4.45, 4.496, 4.52, 4.55, 4.57, 4.60, 4.62, 4.64, 4.66, 4.677, 4.70, 4.71,
+                                         4.73, 4.75, 4.76, 4.78, 4.79, 4.809};
+        const double tf_us = 1.106;
         double R8 = SONIC_SCHED_LONE8_RATIO, SLOW = SONIC_SCHED_STAGED_SLOWDOWN;
         if (const char* e = getenv("SONIC_SCHED_LONE8_RATIO")) R8 = atof(e);    // (tuning runs)
         if (const char* e = getenv("SONIC_SCHED_STAGED_SLOWDOWN")) SLOW = atof(e);
         double tk[33];
-        for (int k = 1; k <= 32; k++) tk[k] = tk_us[k] / 1.21 * SLOW;
+        for (int k = 1; k <= 32; k++) tk[k] = tk_us[k] / tf_us * SLOW;
+        double MARGIN = 1.0;
+        if (const char* e = getenv("SONIC_SCHED_TIER_MARGIN")) MARGIN = atof(e);
         double QOV = SONIC_SCHED_QUEUE_OVERHEAD;
         if (const char* e = getenv("SONIC_SCHED_QUEUE_OVERHEAD")) QOV = atof(e);
         const double RS = tk[1], T32 = tk[32] * QOV;
@@ -1285,7 +1288,9 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         for (double T = chain[0] * 1.02; T < chain[0] * 60.0; T *= 1.03) {
             int E1 = 0, E2 = 0;
             if (can_excl) {
-                const long long n1 = count_above(T / R8), n12 = count_above(T / RS);
+                // (the predicted order of the longest chains is not exact: chains down to MARGIN of a tier's
+                // threshold are taken into the tier as well)
+                const long long n1 = count_above(MARGIN * T / R8), n12 = count_above(MARGIN * T / RS);
                 E1 = (int)((n1 + wps / 2 - 1) / (wps / 2));
                 if (force1 >= 0) E1 = force1;
                 const long long in1 = std::min<long long>((long long)E1 * (wps / 2), n);
@@ -1315,7 +1320,9 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
             for (long long i = 0; i < nl1; i += wps / 2) have += (wps / 2) * std::max(0.0, T - chain[i]);
             for (long long i = nl1; i < nl; i += wps) have += wps * std::max(0.0, T - chain[i] * R8);
             const double queue = have > 0.0 ? T * need / have : (pos < n ? 1e300 : 0.0);
-            const double span = T > queue ? T : queue;
+            // (when the budgets run out of warps the queue starts with chains that are too long for a full warp)
+            const double head = pos < n ? chain[pos] * tk[32] : 0.0;
+            const double span = std::max(std::max(T, queue), head);
             if (span < best_span) { best_span = span; best_T = T; best_E1 = E1; best_E2 = E2; }
             if (queue <= T) break;        // larger T only makes the deadline later
         }
