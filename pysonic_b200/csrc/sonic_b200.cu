@@ -327,11 +327,12 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     }
 }
 
-// Fused cycle averaging.  A warp works through a contiguous range of output points; the capacitance
-// profile of the current point is staged in shared memory and reused for every coverage fraction.
-// Every table of the output is laid out [point][fs], so the (point, fs) entries a warp produces one
-// after the other are consecutive in memory: lane k keeps the results of the k-th entry of the current
-// run of 32 in registers, and a full run is written with one coalesced 256-byte store per table.
+// Fused cycle averaging.  A warp works through a contiguous range of (point, fs) entries -- a multiple of 32, sized
+// on the host so that every SM gets a few dozen ranges whatever the shape of the lookup (many points x one coverage
+// fraction, or few points x 100 fractions); the capacitance profile of the current point is staged in shared memory
+// and reused for every coverage fraction of the range.  Every table of the output is laid out [point][fs], so the
+// entries a warp produces one after the other are consecutive in memory: lane k keeps the results of the k-th entry
+// of the current run of 32 in registers, and a full run is written with one coalesced 256-byte store per table.
 struct SonicAvgArgs {
     const double* zbuf;        // [n_traj][1000] last-cycle deflections
     const int* ia_out;         // [n_out_all] radius entry of every output point (its own Cm0)
@@ -344,7 +345,8 @@ struct SonicAvgArgs {
     const int* sel;            // [n] output points of this launch (one neuron of a multi-neuron plan), or null
     double* out;               // [nvar][n][nfs]
     long long n;
-    int nfs, nov, pts_per_chunk;
+    int nfs, nov;
+    long long entries_per_chunk;   // multiple of 32
 };
 
 template <int NID, bool OVT>
@@ -358,17 +360,20 @@ __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(Son
     const int nvar = 1 + 2 * nov + NR;          // V, (A_Vk, phi_Vk) per overtone, rates
     double* cm = cm_s[warp];
     const long long n = a.n;
-    const long long nchunks = (n + a.pts_per_chunk - 1) / a.pts_per_chunk;
+    const long long total = n * nfs, epc = a.entries_per_chunk;
+    const long long nchunks = (total + epc - 1) / epc;
     const long long nwarps = (long long)gridDim.x * SONIC_AVG_WARPS;
     for (long long chunk = (long long)blockIdx.x * SONIC_AVG_WARPS + warp; chunk < nchunks; chunk += nwarps) {
-        const long long p_first = chunk * a.pts_per_chunk;
-        const long long p_last = (p_first + a.pts_per_chunk < n) ? p_first + a.pts_per_chunk : n;
-        long long e_run = p_first * nfs;        // first entry (point * nfs + fs index) of the current run
+        const long long e_first = chunk * epc;
+        const long long e_last = (e_first + epc < total) ? e_first + epc : total;
+        long long e_run = e_first;              // first entry (point * nfs + fs index) of the current run
         int fill = 0;                           // entries of the run computed so far
         double keep[NV];                        // this lane's entry of the run, one value per table
 #pragma unroll
         for (int v = 0; v < NV; v++) keep[v] = 0.0;
-        for (long long pt = p_first; pt < p_last; pt++) {
+        long long e = e_first;
+        int j0 = (int)(e_first % nfs);
+        for (long long pt = e_first / nfs; e < e_last; pt++, j0 = 0) {
             const long long g = a.sel ? a.sel[pt] : pt;         // among all output points of the plan
             const long long u = a.umap ? a.umap[g] : g;         // trajectory the point reads
             const SonicBls b = a.radii[a.ia_out[g]];
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(Son
             __syncwarp();
             for (int k = lane; k < SONIC_NPC; k += 32) cm[k] = sonic_capacitance(a2, b.Delta, b.Cm0, z[k]);
             __syncwarp();
-            for (int j = 0; j < nfs; j++) {
+            const int j_end = (e_last - e < nfs - j0) ? j0 + (int)(e_last - e) : nfs;
+            for (int j = j0; j < j_end; j++, e++) {
                 const double x = a.fs[j];
                 double acc[NV];
 #pragma unroll
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(Son
                     for (int v = 0; v < NV; v++) keep[v] = bad ? nan("") : acc[v];
                 }
                 fill++;
-                const bool last = (pt + 1 == p_last) && (j + 1 == nfs);
+                const bool last = e + 1 == e_last;
                 if (fill == 32 || last) {
                     // one store per table: slot v of `keep` is table v (V, overtone pairs) or, past the
                     // overtone slots, rate v - 2 (MOV - nov)
@@ -901,13 +907,15 @@ static cudaError_t launch_average(SonicPlan* p, int k) {
     a.n = p->n_out_k[k];
     a.nfs = p->nfs; a.nov = p->nov;
     if (a.n == 0) return cudaSuccess;
-    // points per warp chunk: whole points, a multiple of 32 entries (full 256-byte runs)
+    // entries per warp range: a multiple of 32 (full 256-byte runs), about 32 ranges per SM
     {
-        int g = 32, m = p->nfs % 32;
-        while (m) { const int t = g % m; g = m; m = t; }      // gcd(32, nfs)
-        a.pts_per_chunk = 32 / g;
+        const long long total = a.n * p->nfs;
+        long long m = total / (32LL * 148 * 32);
+        if (m < 1) m = 1;
+        a.entries_per_chunk = 32 * m;
     }
-    long long blocks = ((a.n + a.pts_per_chunk - 1) / a.pts_per_chunk + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
+    const long long nchunks = (a.n * p->nfs + a.entries_per_chunk - 1) / a.entries_per_chunk;
+    long long blocks = (nchunks + SONIC_AVG_WARPS - 1) / SONIC_AVG_WARPS;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
     if (p->nov) sonic_average_kernel<NID, true><<<(int)blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(a);
     else sonic_average_kernel<NID, false><<<(int)blocks, 32 * SONIC_AVG_WARPS, 0, p->stream>>>(a);

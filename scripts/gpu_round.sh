@@ -18,6 +18,9 @@ python tools/gpu_offnode.py > $OUT/offnode_$TAG.json 2> $OUT/offnode_$TAG.err; e
 python tools/gpu_overtones.py $TAG > $OUT/overtones_$TAG.log 2>&1; echo "overtones rc=$?"
 python tools/gpu_make_sim_tables.py > $OUT/sim_tables_$TAG.log 2>&1; echo "tables rc=$?"
 python tools/gpu_kprobe.py $TAG > $OUT/kprobe_$TAG.json 2> $OUT/kprobe_$TAG.err; echo "kprobe rc=$?"
+# calibration of the scheduler: tick of lone lanes (register-resident run / staged tick) and of staged warps with k busy lanes
+{ python tools/gpu_lone_rates.py | tail -1; SONIC_NESTED=0 python tools/gpu_lone_rates.py | tail -1; python tools/gpu_tk.py; } > $OUT/ticks_$TAG.jsonl 2> $OUT/ticks_$TAG.err; echo "ticks rc=$?"
+python tools/gpu_wl.py $TAG > $OUT/workloads_$TAG.json 2> $OUT/workloads_$TAG.err; echo "workloads rc=$?"
 if [ "${NO_NCU:-0}" = "0" ]; then
   CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras"
   $CMD > $OUT/plain_launches_$TAG.log 2>&1 && \

@@ -4,7 +4,7 @@
     effDerivatives :280-315; Lookup.project / interpolate1D, lookups.py:259-333) run on tables built by the
     reference itself (the grid fixtures of this directory written back as lookup pickles).  Build container only.
 
-        python tests/golden/make_sim_goldens.py
+        python tests/golden/make_sim_goldens.py [--tables-only | --ulp NEURON ...]
 '''
 import json
 import os
@@ -47,6 +47,15 @@ for name in ('STN', 'TC'):
     if not os.path.isfile(os.path.join(HERE, fname)):
         mg._grid_to_npz(fname, name, [32e-9], [500e3], SIM_AMPS, mg.default_charges(name), [1.0])
 
+# the reference's own reproducibility for the spike-count check: a table re-built with the drive amplitude changed by
+# +-2 ulp (python tests/golden/make_sim_goldens.py --ulp RE [TC ...])
+if '--ulp' in sys.argv:
+    for name in sys.argv[sys.argv.index('--ulp') + 1:]:
+        for sc, tag in ((1.0 + 4.440892098500626e-16, '_ulp_up'), (1.0 - 4.440892098500626e-16, '_ulp_dn')):
+            fname = f'sim_tab_{name}{tag}.npz'
+            if not os.path.isfile(os.path.join(HERE, fname)):
+                mg._grid_to_npz(fname, name, [32e-9], [500e3], SIM_AMPS, mg.default_charges(name), [1.0], sc)
+    sys.exit(0)
 if '--tables-only' in sys.argv:
     sys.exit(0)
 out = {'cases': []}

@@ -169,7 +169,8 @@ def extras(tag):
     import shutil
     for src, dst in ((f'parity_{tag}.json', f'{tag}_parity.json'), (f'configs_{tag}.json', f'{tag}_configs_c3_c4_c5.json'),
                      (f'offnode_{tag}.json', f'{tag}_offnode.json'), (f'overtones_{tag}.json', f'{tag}_overtones_lookup.json'),
-                     (f'kprobe_{tag}.json', f'{tag}_kprobe.json')):
+                     (f'kprobe_{tag}.json', f'{tag}_kprobe.json'), (f'ticks_{tag}.jsonl', f'{tag}_tick_calibration.jsonl'),
+                     (f'workloads_{tag}.json', f'{tag}_workloads.json')):
         p = os.path.join(OUT, src)
         if os.path.isfile(p) and os.path.getsize(p) > 0:
             shutil.copyfile(p, os.path.join(PROF, dst))
