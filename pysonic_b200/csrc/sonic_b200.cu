@@ -51,6 +51,9 @@
 #ifndef SONIC_WIDEN
 #define SONIC_WIDEN 1
 #endif
+#ifndef SONIC_LONE_PARK
+#define SONIC_LONE_PARK 1
+#endif
 /* relative to the tick of a lone lane in the register-resident run with four such warps on its SM (1.106 us): the same with
    eight warps on the SM (1.44 us) */
 #ifndef SONIC_SCHED_LONE8_RATIO
@@ -131,6 +134,7 @@ struct SonicJob {
     const int* block_group;    // [blocks]: SM group of a block whose SM hosts nothing but one-point warps, else -1
     int* group_left;           // [groups]: warps of the group still on their initial chain
     int widen;                 // 1 = budgeted warps go to full width once their initial points are done
+    int lone_park;             // 1 = a one-point warp whose chain is done waits for its SM instead of taking queue points
 };
 
 __constant__ SonicTables c_tables;
@@ -237,6 +241,12 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
                 left = __shfl_sync(0xffffffffu, left, 0);
             }
             if (left <= 0) cap = 32;
+            else if (job.lone_park && __all_sync(0xffffffffu, pt < 0)) {
+                // the chains still running on this SM are among the longest of the grid: leave them the SM
+                // (a lone lane ticks in 1.1 us with four warps on the SM, 1.44 us with eight)
+                __nanosleep(4000);
+                continue;
+            }
         }
         if (pt < 0 && !exhausted && lane < cap) {
             // (re)fill this lane: its initial point first, then the shared work queue
@@ -1261,7 +1271,14 @@ static int plan_build(int device, const SonicBlsParams* radii, const int32_t* ra
         if (const char* e = getenv("SONIC_SCHED_LONE8_RATIO")) R8 = atof(e);    // (tuning runs)
         if (const char* e = getenv("SONIC_SCHED_STAGED_SLOWDOWN")) SLOW = atof(e);
         double tk[33];
-        for (int k = 1; k <= 32; k++) tk[k] = tk_us[k] / tf_us * SLOW;
+        // (a sparsely populated staged warp next to full-width warps ticks slower than in the calibration runs, where
+        // every warp of the device holds the same number of lanes: 2.2-2.5 us measured for k = 1 against 1.65, 2.8-3.2 us
+        // for k = 2-3 against 2.25-2.70, no difference at full width.  A factor that decays with k, SDEC ~ 3, describes
+        // that, but the schedules it leads to -- more SMs of lone warps -- starve the queue on C2, FHnode and TC:
+        // 1.49 / 3.31 / 1.31 s against 1.26 / 2.67 / 1.07 s with the uniform factor, which is the default)
+        double SDEC = 1e9;
+        if (const char* e = getenv("SONIC_SCHED_SLOWDOWN_DECAY")) SDEC = atof(e);
+        for (int k = 1; k <= 32; k++) tk[k] = tk_us[k] / tf_us * (1.0 + (SLOW - 1.0) * exp(-(k - 1) / SDEC));
         double MARGIN = 1.0;
         if (const char* e = getenv("SONIC_SCHED_TIER_MARGIN")) MARGIN = atof(e);
         double QOV = SONIC_SCHED_QUEUE_OVERHEAD;
@@ -1516,6 +1533,8 @@ int sonic_plan_launch(SonicPlan* p) {
     job.block_group = p->d_block_group; job.group_left = p->d_group_left;
     job.widen = SONIC_WIDEN;
     if (const char* e = getenv("SONIC_WIDEN")) job.widen = atoi(e);      // (tuning runs)
+    job.lone_park = SONIC_LONE_PARK;
+    if (const char* e = getenv("SONIC_LONE_PARK")) job.lone_park = atoi(e);
     cudaEvent_t* ev = p->ws->ev;
     p->result_on_host = false;
     CUDA_TRY(cudaMemcpyAsync(p->d_counter, p->d_counter0, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, p->stream));
