@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     int init_left = __popc(__ballot_sync(0xffffffffu, q_init >= 0));
     const int group = job.block_group ? job.block_group[blockIdx.x] : -1;
     bool released = init_left == 0;        // nothing (left) to wait for
+    int park_spins = 0;
     if (released && group >= 0 && cap > 0 && cap < 32 && lane == 0) atomicSub(&job.group_left[group], 1);
     if (cap == 0) {
         // Parked warp: it shares its SM with the very longest chains of the grid, which then have a
@@ -241,9 +242,11 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
                 left = __shfl_sync(0xffffffffu, left, 0);
             }
             if (left <= 0) cap = 32;
-            else if (job.lone_park && __all_sync(0xffffffffu, pt < 0)) {
+            else if (job.lone_park && park_spins < 2000000 && __all_sync(0xffffffffu, pt < 0)) {
                 // the chains still running on this SM are among the longest of the grid: leave them the SM
-                // (a lone lane ticks in 1.1 us with four warps on the SM, 1.44 us with eight)
+                // (a lone lane ticks in 1.1 us with four warps on the SM, 1.44 us with eight).  Bounded wait
+                // (~10 s): never spin forever on the assumption that the whole grid is resident.
+                park_spins++;
                 __nanosleep(4000);
                 continue;
             }

@@ -78,20 +78,28 @@ def main():
         n_eng = spikes_with_table(name, os.path.join(tdir, fn), amps)
         r = {'neuron': name, 'a': 32e-9, 'f': 500e3, 'fixture': fixture, 'amplitudes_Pa': amps,
              'spikes_reference_table': n_ref, 'spikes_engine_table': n_eng, 'identical': n_ref == n_eng}
-        # the reference's own spread: tables it built with the drive amplitude changed by +-2 ulp
-        variants = []
+        # the reference's own spread: (1) the same simulation on the same table a second time -- its event-driven solver
+        # (scipy's non-re-entrant LSODA object) is not reproducible from call to call for every neuron, SWnode at
+        # >= 200 kPa gives 0 or 1 spikes, or leaves the charge range, depending on what ran before in the process --
+        # and (2) tables it built with the drive amplitude changed by +-2 ulp
+        variants = [spikes_with_table(name, refp, amps)]
+        r['spikes_reference_table_second_run'] = variants[0]
         for tag in ('_ulp_up', '_ulp_dn'):
             vf = fixture[:-4] + tag + '.npz'
             if os.path.isfile(os.path.join(GOLD, vf)):
                 vp = os.path.join(tmp, f'{name}{tag}.pkl')
                 fixture_pickle(vf, vp)
                 variants.append(spikes_with_table(name, vp, amps))
-        if variants:
-            r['spikes_reference_table_ulp_reruns'] = variants
-            r['reference_reproduces_itself'] = all(v == n_ref for v in variants)
-            r['within_reference_spread'] = all(
-                min([n_ref[i]] + [v[i] for v in variants]) <= n_eng[i] <= max([n_ref[i]] + [v[i] for v in variants])
-                for i in range(len(amps)) if n_eng[i] is not None and n_ref[i] is not None)
+        r['spikes_reference_table_ulp_reruns'] = variants[1:]
+        r['reference_reproduces_itself'] = all(v == n_ref for v in variants)
+
+        def spread(i):
+            vals = [x[i] for x in [n_ref] + variants if x[i] is not None]
+            return (min(vals), max(vals), any(x[i] is None for x in [n_ref] + variants)) if vals else (None, None, True)
+        r['within_reference_spread'] = all(
+            (n_eng[i] is None and spread(i)[2]) or
+            (n_eng[i] is not None and spread(i)[0] is not None and spread(i)[0] <= n_eng[i] <= spread(i)[1])
+            for i in range(len(amps)))
         print(json.dumps(r), flush=True)
         res.append(r)
     if len(sys.argv) > 2:
