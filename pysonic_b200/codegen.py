@@ -25,8 +25,39 @@ HEADER = '''// GENERATED FILE -- do not edit.  Produced by pysonic_b200/codegen.
 #define SONIC_N_NEURONS {nn}
 #define SONIC_MAX_RATES {maxr}
 
+// Arithmetic of the rate expressions.  The reference's formulas are compiled as they are written (neurons.py), on a
+// wrapper type: a division is a multiplication by a refined hardware reciprocal (<= 2 ulp; 1 / 0 = inf, 1 / inf = 0),
+// the exponential is the branch-free one of the integrator
+// (sonic_exp, 1-2 ulp) inside its range and the library's outside.  The averaging kernel evaluates every rate of the
+// neuron at 1000 samples x every coverage fraction of every point: on the STN coverage sweep (19 tables) this is the
+// second largest kernel of the run.  (sonic_core.h is included before this header.)
+struct rd {{
+    double v;
+    __device__ __forceinline__ rd(double x) : v(x) {{}}
+}};
+static __device__ __forceinline__ rd operator+(rd a, rd b) {{ return rd(a.v + b.v); }}
+static __device__ __forceinline__ rd operator-(rd a, rd b) {{ return rd(a.v - b.v); }}
+static __device__ __forceinline__ rd operator*(rd a, rd b) {{ return rd(a.v * b.v); }}
+// (sonic_rcp is for the integrator's tame arguments: its refinement turns 1 / 0 and 1 / inf into NaN, and the rates do
+// reach exp() = inf and x / 0 at their singular points: this one keeps the hardware seed there, without a branch)
+static __device__ __forceinline__ double rate_rcp(double x) {{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    const double r2 = fma(r, e, r);
+    return r2 == r2 ? r2 : r;          // 1 / 0 = inf and 1 / inf = 0 as the hardware seed gives them
+}}
+static __device__ __forceinline__ rd operator/(rd a, rd b) {{ return rd(a.v * rate_rcp(b.v)); }}
+static __device__ __forceinline__ rd operator-(rd a) {{ return rd(-a.v); }}
+static __device__ __forceinline__ rd operator+(rd a) {{ return a; }}
+static __device__ __forceinline__ bool operator<(rd a, rd b) {{ return a.v < b.v; }}
+static __device__ __forceinline__ bool operator>(rd a, rd b) {{ return a.v > b.v; }}
+static __device__ __forceinline__ bool operator<=(rd a, rd b) {{ return a.v <= b.v; }}
+static __device__ __forceinline__ bool operator>=(rd a, rd b) {{ return a.v >= b.v; }}
+static __device__ __forceinline__ rd exp(rd x) {{ return rd(fabs(x.v) < 690.0 ? sonic_exp(x.v) : ::exp(x.v)); }}
 // x / (exp(x / y) - 1): naive form of the reference (pneuron.py:351-354), 0/0 at x = 0 kept.
-static __device__ __forceinline__ double vtrap(double x, double y) {{ return x / (exp(x / y) - 1); }}
+static __device__ __forceinline__ rd vtrap(rd x, rd y) {{ return x / (exp(x / y) - 1); }}
 
 template <int ID> struct SonicRates;
 
@@ -47,23 +78,24 @@ def gen_neuron(nid, name):
     spec = NEURON_SPECS[name]
     lines = [f'// ---- {name} ----', f'template <> struct SonicRates<{nid}> {{',
              f'    static constexpr int N = {len(spec_rate_names(name))};',
-             '    static __device__ __forceinline__ void eval(const double Vm, double* r) {']
+             '    static __device__ __forceinline__ void eval(const double Vm_, double* r) {',
+             '        const rd Vm(Vm_);']
     for k, v in spec['consts'].items():
-        lines.append(f'        const double {k} = {_fmt(v)};')
+        lines.append(f'        const rd {k}({_fmt(v)});')
     for item in spec['kin']:
         for st in item.pre:
-            lines.append(f'        const double {st};')
+            lines.append(f'        const rd {st};')
     i = 0
     for item in spec['kin']:
         if isinstance(item, Gate):
-            lines.append(f'        const double inf_{item.key} = {item.xinf};')
-            lines.append(f'        const double tau_{item.key} = {item.tau};')
-            lines.append(f'        r[{i}] = inf_{item.key} / tau_{item.key};')
-            lines.append(f'        r[{i + 1}] = (1 - inf_{item.key}) / tau_{item.key};')
+            lines.append(f'        const rd inf_{item.key} = {item.xinf};')
+            lines.append(f'        const rd tau_{item.key} = {item.tau};')
+            lines.append(f'        r[{i}] = rd(inf_{item.key} / tau_{item.key}).v;')
+            lines.append(f'        r[{i + 1}] = rd((1 - inf_{item.key}) / tau_{item.key}).v;')
             i += 2
         else:
             assert isinstance(item, Rate)
-            lines.append(f'        r[{i}] = {item.expr};')
+            lines.append(f'        r[{i}] = rd({item.expr}).v;')
             i += 1
     for k in spec['consts']:
         lines.append(f'        (void){k};')

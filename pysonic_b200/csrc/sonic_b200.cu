@@ -73,8 +73,8 @@
 
 #include "../../include/sonic_b200.h"
 #include "generated/cost_table.h"
-#include "generated/neuron_rates.cuh"
 #include "sonic_core.h"
+#include "generated/neuron_rates.cuh"
 #include "sonic_quad.h"
 
 // ---------------------------------------------------------------------------------------
@@ -104,6 +104,9 @@ static int set_err(int code, const char* fmt, ...) {
 // device code
 // ---------------------------------------------------------------------------------------
 #define SONIC_AVG_WARPS 4
+#ifndef SONIC_AVG_MIN_BLOCKS
+#define SONIC_AVG_MIN_BLOCKS 1
+#endif
 #define SONIC_HIST_BYTES (SONIC_H_SIZE * SONIC_BLOCK * sizeof(double))
 
 struct SonicJob {
@@ -363,7 +366,7 @@ struct SonicAvgArgs {
 };
 
 template <int NID, bool OVT>
-__global__ void __launch_bounds__(32 * SONIC_AVG_WARPS) sonic_average_kernel(SonicAvgArgs a) {
+__global__ void __launch_bounds__(32 * SONIC_AVG_WARPS, SONIC_AVG_MIN_BLOCKS) sonic_average_kernel(SonicAvgArgs a) {
     constexpr int NR = SonicRates<NID>::N;
     constexpr int MOV = OVT ? SONIC_MAX_OVERTONES : 0;      // overtone slots (none in the common instantiation)
     constexpr int NV = 1 + 2 * MOV + NR;
