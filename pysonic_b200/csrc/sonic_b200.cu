@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     // one-point warps (group >= 0) only when every warp of the SM has got there -- until then it keeps taking single
     // points from the queue, so that the SM runs one instruction stream at a time.
     bool is_init = false;                  // this lane works on one of the warp's initial points
+    bool init_done_now = false;            // ... and has just finished it (or found it without equilibrium)
     int init_left = __popc(__ballot_sync(0xffffffffu, q_init >= 0));
     const int group = job.block_group ? job.block_group[blockIdx.x] : -1;
     bool released = init_left == 0;        // nothing (left) to wait for
@@ -238,6 +239,14 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
     }
 
     while (true) {
+        if (!released) {
+            init_left -= __popc(__ballot_sync(0xffffffffu, init_done_now));
+            init_done_now = false;
+            if (init_left <= 0) {
+                released = true;
+                if (group >= 0 && lane == 0) atomicSub(&job.group_left[group], 1);
+            }
+        }
         if (released && cap < 32 && job.widen) {
             int left = 0;
             if (group >= 0) {
@@ -281,6 +290,8 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
                     job.nfe[pt] = 0; job.nje[pt] = 0; job.nsteps[pt] = 0;
                     job.tpoint[pt] = 0.0;
                     pt = -1;
+                    init_done_now = is_init;
+                    is_init = false;
                 } else {
                     sonic_lane_start(s, H, p, f, z0, sink);
                 }
@@ -332,14 +343,10 @@ __global__ void __launch_bounds__(SONIC_BLOCK, SONIC_BLOCKS_PER_SM) sonic_integr
             job.tpoint[pt] = (double)(sonic_globaltimer() - t_start) * 1e-9;
             pt = -1;
         }
-        if (!released) {
-            init_left -= __popc(__ballot_sync(0xffffffffu, fin && is_init));
-            if (init_left <= 0) {
-                released = true;
-                if (group >= 0 && lane == 0) atomicSub(&job.group_left[group], 1);
-            }
+        if (fin) {
+            init_done_now = is_init;
+            is_init = false;
         }
-        if (fin) is_init = false;
     }
 }
 
