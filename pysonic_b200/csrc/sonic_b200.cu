@@ -3,12 +3,17 @@
 // Kernels
 //   sonic_z0_kernel         initial quasi-static deflection of every point (one thread/point)
 //   sonic_integrate_kernel  persistent batched integrator: one lane per grid point, lanes
-//                           refill themselves from a cost-sorted work queue; every tick = one
-//                           warp-convergent RHS evaluation + per-lane controller bookkeeping;
-//                           periodic-convergence test on the fly against the previous cycle
+//                           refill themselves from a cost-sorted work queue; wide warps: every tick =
+//                           one warp-convergent RHS evaluation + staged per-lane bookkeeping; a lane
+//                           alone in its warp: register-resident BDF runs (sonic_core.h); periodic-
+//                           convergence test on the fly against the previous cycle
 //   sonic_average_kernel    fused cycle averaging: Z(t) -> Cm -> per coverage fraction V(t)
-//                           -> generated neuron rate functions -> warp-shuffle means
-//   sonic_rates_kernel      elementwise / mean evaluation of the generated rate functions
+//                           -> generated neuron rate functions -> warp-shuffle means -> coalesced stores
+//   sonic_rates_kernel, sonic_mean_rates_kernel   elementwise / mean evaluation of the rate functions
+//   sonic_relcm_kernel      relative capacitance profiles of the last cycle (run_Cm_lookups)
+//   sonic_pmavg_kernel      intermolecular pressure by QUADPACK QAGS (sonic_quad.h), for the Lennard-Jones fit
+//   sonic_simulate_kernel   SONIC simulations on the tables (effective system, one thread per simulation)
+//   sonic_stats_kernel      device-side reduction of the per-point counters
 //   sonic_dfma_kernel       FP64 FMA throughput microbenchmark (roofline denominator)
 //
 // Host side: plan objects (device buffers + stream + events), cost model for the work queue
