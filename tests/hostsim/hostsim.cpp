@@ -173,6 +173,43 @@ double hostsim_quad(int kind, double a, double b, int* last) {
     return sonic_qags(f, a, b, last);
 }
 
+// Decision-equivalence of the two shortcuts of the step-size heuristics (sonic_core.h): for BDF order nq and
+// error estimates (dsm, ddn, dup; dup < 0: no candidate for an order increase)
+//   out[0] = 1 if sonic_select's shortcut fires ("every candidate is certainly below 1.1")
+//   out[1] = the largest of the three step-size candidates, computed in full
+//   out[2] = 1 if sonic_method_switch_decide's shortcut fires for (dsm, pdnorm * |h| = pdh)
+//   out[3] = 1 if the full method-switch test (shortcut disabled by calling with dsm > 1 guard bypassed) says "switch"
+void hostsim_shortcuts(int nq, double dsm, double ddn, double dup, double pdh, double pnorm, double* out) {
+    if (!g_tab_ready) {
+        sonic_fill_tables(&g_tab);
+        g_tab_ready = 1;
+    }
+    const SonicTables* T = &g_tab;
+    const int l = nq + 1;
+    out[0] = (dsm > T->thr_sm[nq - 1] && (nq == 1 || ddn > T->thr_dn[nq - 1]) && (dup < 0.0 || dup > T->thr_up[nq - 1])) ? 1.0 : 0.0;
+    const double rhsm = 1.0 / (1.2 * pow(dsm, 1.0 / l) + 0.0000012);
+    const double rhdn = nq == 1 ? 0.0 : 1.0 / (1.3 * pow(ddn, 1.0 / nq) + 0.0000013);
+    const double rhup = (dup < 0.0 || l == SONIC_MXORDS + 1) ? 0.0 : 1.0 / (1.4 * pow(dup, 1.0 / (l + 1)) + 0.0000014);
+    out[1] = fmax(rhsm, fmax(rhdn, rhup));
+    // method-switch test of a BDF step: the shortcut, and the full comparison it stands for
+    out[2] = (dsm <= 1.0 && T->sm1[nq - 1] < 0.8 * pdh) ? 1.0 : 0.0;
+    {
+        const double exsm = 1.0 / l;
+        double rh1 = 1.0 / (1.2 * pow(dsm * T->c21[nq - 1], exsm) + 0.0000012);
+        double rh1it = 2.0 * rh1;
+        if (pdh * rh1 > 0.00001) rh1it = T->sm1[nq - 1] / pdh;
+        rh1 = fmin(rh1, rh1it);
+        const double rh2 = 1.0 / (1.2 * pow(dsm, exsm) + 0.0000012);
+        bool sw = !(rh1 * 5.0 < 5.0 * rh2);
+        if (sw) {
+            const double alpha = fmax(0.001, rh1);
+            const double dm1 = pow(alpha, exsm) * (dsm * T->c21[nq - 1]);
+            if (dm1 <= 1000.0 * SONIC_UROUND * pnorm) sw = false;
+        }
+        out[3] = sw ? 1.0 : 0.0;
+    }
+}
+
 long hostsim_tables_size(void) { return (long)(sizeof(SonicTables) / sizeof(double)); }
 
 void hostsim_tables(double* out) {

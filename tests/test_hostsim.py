@@ -294,3 +294,32 @@ def test_tick_drivers_are_bit_identical(hostsim):
             assert r['z'].tobytes() == res[0]['z'].tobytes() and r['nfe'] == res[0]['nfe'] and r['ncycles'] == res[0]['ncycles']
     finally:
         hostsim.set_driver(0)
+
+
+def test_step_size_shortcuts_are_decision_equivalent(hostsim):
+    ''' The integrator settles most order selections and method-switch tests without taking a power
+        (sonic_select: every candidate certainly below 1.1; sonic_method_switch_decide: stiff at this step size).
+        Whenever a shortcut fires, the full computation must come to the same decision: checked on random error
+        estimates, dense around the tabulated levels. '''
+    lib = hostsim.lib
+    out = (ctypes.c_double * 4)()
+    rng = np.random.default_rng(3)
+    fired_sel = fired_ms = 0
+    for _ in range(40000):
+        nq = int(rng.integers(1, 6))
+        l = nq + 1
+        # error estimates spread over decades, half of them within a few percent of the level where the candidate is 1.1
+        lev = [((1 / 1.1 - c * 1e-6) / c) ** e for c, e in ((1.2, l), (1.3, nq), (1.4, l + 1))]
+        d = [float(lv * (1 + rng.normal(0, 0.02)) if rng.random() < 0.5 else 10 ** rng.uniform(-12, 0)) for lv in lev]
+        dsm, ddn, dup = min(abs(d[0]), 1.0), abs(d[1]), abs(d[2]) if rng.random() < 0.8 else -1.0
+        pdh = float(10 ** rng.uniform(-3, 3))
+        pnorm = float(10 ** rng.uniform(0, 8))
+        lib.hostsim_shortcuts(ctypes.c_int(nq), ctypes.c_double(dsm), ctypes.c_double(ddn), ctypes.c_double(dup),
+                              ctypes.c_double(pdh), ctypes.c_double(pnorm), out)
+        if out[0]:
+            fired_sel += 1
+            assert out[1] < 1.1, (nq, dsm, ddn, dup, out[1])
+        if out[2]:
+            fired_ms += 1
+            assert not out[3], (nq, dsm, pdh)
+    assert fired_sel > 1000 and fired_ms > 5000, (fired_sel, fired_ms)
